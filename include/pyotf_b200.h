@@ -1,0 +1,86 @@
+/* pyotf_b200 -- C ABI of the B200-native PSF/OTF + phase-retrieval engine.
+ *
+ * pyotf (david-hoffman/pyotf) has no FFI layer: its boundary is a Python object API.  This
+ * header is the C boundary *under* our Python mirror of that API (pyotf_b200/otf.py,
+ * phaseretrieval.py, zernike.py); every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is available from
+ *     pyotf_b200_last_error() (thread-local).  No C++ exception crosses this boundary.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it
+ *     unless the function is documented as synchronising.
+ *   - `*_dev` pointers are device pointers owned by the caller (torch allocations in the
+ *     Python host); handles own only their small O(N^2) parameter tables.
+ *   - dtype: 0 = float32 / complex64 ("fp32 mode"), 1 = float64 / complex128 ("fp64 mode").
+ *   - complex arrays are interleaved (re, im).  "unshifted" = numpy.fft.fftfreq order,
+ *     "shifted" = numpy.fft.fftshift order, exactly as the reference returns them.
+ */
+#ifndef PYOTF_B200_H
+#define PYOTF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYOTF_B200_ABI_VERSION 1
+
+enum { PYOTF_F32 = 0, PYOTF_F64 = 1 };
+enum { PYOTF_VEC_NONE = 0, PYOTF_VEC_X = 1, PYOTF_VEC_Y = 2, PYOTF_VEC_Z = 3, PYOTF_VEC_TOTAL = 4 };
+enum { PYOTF_COND_NONE = 0, PYOTF_COND_SINE = 1, PYOTF_COND_HERSCHEL = 2 };
+
+int pyotf_b200_abi_version(void);
+const char* pyotf_b200_last_error(void);
+/* sm count, max dynamic shared memory per block, compute capability of `device` */
+int pyotf_b200_device_query(int device, int* sm_count, int* smem_optin_bytes, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * HanserPSF  (pyotf/otf.py:265-443)
+ * ---------------------------------------------------------------------------------- */
+typedef struct pyotf_hanser_params {
+    double wl, na, ni, res; /* BasePSF.__init__                      otf.py:53-104 */
+    int size;               /* x/y size N (power of two, 32..256 on the fused path)   */
+    int vec_corr;           /* PYOTF_VEC_*                           otf.py:405-417 */
+    int condition;          /* PYOTF_COND_*                          otf.py:396-403 */
+    int dtype;              /* PYOTF_F32 / PYOTF_F64                                  */
+    int support;            /* -1: no user pupil, ideal mask kr <= na/wl is applied
+                               (HanserPSF._gen_pupil, otf.py:346-355);
+                               h >= 0: a user pupil is supplied whose non-zero support is
+                               |f| <= h frequency bins (see pyotf_b200_pupil_support)    */
+} pyotf_hanser_params;
+
+typedef struct pyotf_hanser pyotf_hanser_t;
+
+/* Builds the fp64 pupil-plane geometry on the device (replaces HanserPSF._gen_kr,
+ * otf.py:335-344, and the z-independent factors of _gen_psf, otf.py:392-417). */
+int pyotf_b200_hanser_create(const pyotf_hanser_params* params, void* stream, pyotf_hanser_t** out);
+int pyotf_b200_hanser_destroy(pyotf_hanser_t* h);
+/* K = edge of the compact support box, f0 = its first frequency bin, nvec = 1|2|6 */
+int pyotf_b200_hanser_info(const pyotf_hanser_t* h, int* K, int* f0, int* nvec);
+/* copies the geometry tables out (any pointer may be NULL): kz [K*K] f64, amp [nvec*K*K] in
+ * the handle's dtype, mask [K*K] u8 -- used by the parity tests for the edge predicates */
+int pyotf_b200_hanser_tables(const pyotf_hanser_t* h, double* kz_dev, void* amp_dev, unsigned char* mask_dev,
+                             void* stream);
+
+/* Largest |frequency bin| at which an unshifted size x size complex128 pupil is non-zero.
+ * SYNCHRONISES the stream (returns one int to the host). */
+int pyotf_b200_pupil_support(const void* pupil_c128_dev, int size, int* hmax_host, void* stream);
+
+/* Gathers `batch` unshifted size x size complex128 pupils into the handle's compact centred
+ * K x K layout and dtype (the `pupil_base` argument of _gen_psf, otf.py:362-389). */
+int pyotf_b200_hanser_pack_pupil(const pyotf_hanser_t* h, const void* pupil_c128_dev, int batch,
+                                 void* pupilc_out_dev, void* stream);
+
+/* K1 -- HanserPSF._gen_psf + BasePSF.PSFi  (otf.py:362-428, 204-207).
+ *   z_dev        [nz] float64 plane positions (HanserPSF.zrange, otf.py:296-333)
+ *   pupilc_dev   NULL (ideal pupil) or [batch] compact pupils, `pupil_stride` elements apart
+ *                (0 = one pupil shared by the whole batch)
+ *   psfa_out_dev NULL or [batch][nvec][nz][N][N] complex, spatially shifted
+ *   psfi_out_dev NULL or [batch][nz][N][N] real, spatially shifted                         */
+int pyotf_b200_hanser_psf(const pyotf_hanser_t* h, const double* z_dev, int nz, const void* pupilc_dev,
+                          int batch, long long pupil_stride, void* psfa_out_dev, void* psfi_out_dev,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYOTF_B200_H */

@@ -1,0 +1,149 @@
+"""Host-side plumbing between the Python API and the C ABI: precision mode, device tensors,
+streams and handle caches.  torch is used for device memory / streams only."""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import _lib
+
+_VEC = {"none": 0, "x": 1, "y": 2, "z": 3, "total": 4}
+_COND = {"none": 0, "sine": 1, "herschel": 2}
+
+_state = threading.local()
+_default_precision = os.environ.get("PYOTF_B200_PRECISION", "fp64")
+
+
+def set_precision(mode):
+    """Select "fp32" (complex64 kernels, rel. L2 <= 1e-5 vs pyotf) or "fp64" (<= 1e-11)."""
+    global _default_precision
+    if mode not in ("fp32", "fp64"):
+        raise ValueError("precision must be 'fp32' or 'fp64'")
+    _default_precision = mode
+
+
+def get_precision():
+    return _default_precision
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise _lib.Pyotf_b200Error("pyotf_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch
+
+
+def dtype_code(precision):
+    return 0 if precision == "fp32" else 1
+
+
+def torch_dtypes(precision):
+    torch = _torch()
+    return (torch.float32, torch.complex64) if precision == "fp32" else (torch.float64, torch.complex128)
+
+
+def stream_ptr():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class HanserHandle:
+    """Owns one pyotf_hanser_t (device geometry tables for fixed optics / size / dtype / support)."""
+
+    def __init__(self, wl, na, ni, res, size, vec_corr, condition, precision, support):
+        lib = _lib.load()
+        _torch()
+        p = _lib.HanserParams(float(wl), float(na), float(ni), float(res), int(size), _VEC[vec_corr],
+                              _COND[condition], dtype_code(precision), int(support))
+        h = C.c_void_p()
+        _lib.check(lib.pyotf_b200_hanser_create(C.byref(p), stream_ptr(), C.byref(h)))
+        self._h, self.precision, self.size = h, precision, int(size)
+        K, f0, nvec = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(lib.pyotf_b200_hanser_info(h, C.byref(K), C.byref(f0), C.byref(nvec)))
+        self.K, self.f0, self.nvec = K.value, f0.value, nvec.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().pyotf_b200_hanser_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def tables(self):
+        """(kz [K,K] f64, amp [nvec,K,K], mask [K,K] u8) device tensors -- for tests."""
+        torch = _torch()
+        rt, _ = torch_dtypes(self.precision)
+        kz = torch.empty((self.K, self.K), dtype=torch.float64, device="cuda")
+        amp = torch.empty((self.nvec, self.K, self.K), dtype=rt, device="cuda")
+        mask = torch.empty((self.K, self.K), dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.load().pyotf_b200_hanser_tables(self._h, ptr(kz), ptr(amp), ptr(mask), stream_ptr()))
+        return kz, amp, mask
+
+    def pack_pupil(self, pupil_dev):
+        """[B,N,N] complex128 unshifted device tensor -> compact [B,K,K] in the handle's dtype."""
+        torch = _torch()
+        _, ct = torch_dtypes(self.precision)
+        B = pupil_dev.shape[0]
+        out = torch.empty((B, self.K, self.K), dtype=ct, device="cuda")
+        _lib.check(_lib.load().pyotf_b200_hanser_pack_pupil(self._h, ptr(pupil_dev), B, ptr(out), stream_ptr()))
+        return out
+
+    def psf(self, z_dev, pupilc=None, batch=1, want_psfa=False, want_psfi=True, psfa_out=None, psfi_out=None):
+        """Run K1.  Returns (psfa or None, psfi or None) as device tensors."""
+        torch = _torch()
+        rt, ct = torch_dtypes(self.precision)
+        nz, N = int(z_dev.numel()), self.size
+        stride = 0
+        if pupilc is not None:
+            if pupilc.dim() == 2:
+                pupilc = pupilc[None]
+            stride = self.K * self.K if pupilc.shape[0] > 1 else 0
+            if pupilc.shape[0] > 1:
+                batch = pupilc.shape[0]
+        if want_psfa and psfa_out is None:
+            psfa_out = torch.empty((batch, self.nvec, nz, N, N), dtype=ct, device="cuda")
+        if want_psfi and psfi_out is None:
+            psfi_out = torch.empty((batch, nz, N, N), dtype=rt, device="cuda")
+        _lib.check(_lib.load().pyotf_b200_hanser_psf(
+            self._h, ptr(z_dev), nz, ptr(pupilc), batch, stride, ptr(psfa_out), ptr(psfi_out), stream_ptr()))
+        return psfa_out, psfi_out
+
+
+_handles = {}
+_handles_lock = threading.Lock()
+
+
+def hanser_handle(wl, na, ni, res, size, vec_corr, condition, precision, support):
+    torch = _torch()
+    key = (float(wl), float(na), float(ni), float(res), int(size), vec_corr, condition, precision, int(support),
+           torch.cuda.current_device())
+    with _handles_lock:
+        h = _handles.get(key)
+        if h is None:
+            if len(_handles) > 64:
+                _handles.clear()
+            h = _handles[key] = HanserHandle(wl, na, ni, res, size, vec_corr, condition, precision, support)
+    return h
+
+
+def pupil_support(pupil_dev):
+    """Largest |frequency bin| where the unshifted [N,N] complex128 device pupil is non-zero (syncs)."""
+    out = C.c_int(0)
+    _lib.check(_lib.load().pyotf_b200_pupil_support(ptr(pupil_dev), int(pupil_dev.shape[-1]), C.byref(out), stream_ptr()))
+    return out.value
+
+
+def to_device_f64(a):
+    torch = _torch()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)), device="cuda")
+
+
+def to_device_c128(a):
+    torch = _torch()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.complex128)), device="cuda")

@@ -1,0 +1,141 @@
+// In-register radix-2/4/8/16 butterflies and small complex helpers (sm_100a).
+//
+// Everything here is templated on the real type T (float / double) and on the transform
+// direction DIR: +1 = inverse (numpy ifft kernel e^{+2 pi i k n / N}), -1 = forward.
+// Outputs are in natural order; there is no normalisation (callers scale).
+//
+// These replace the pocketfft passes behind numpy.fft.ifftn / fftn at
+// pyotf/otf.py:426, pyotf/phaseretrieval.py:124 and pyotf/utils.py:17,22.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pyotf {
+
+template <typename T> struct cplx { T x, y; };
+
+template <typename T> struct vec2;
+template <> struct vec2<float> { using type = float2; };
+template <> struct vec2<double> { using type = double2; };
+
+template <typename T> __device__ __forceinline__ cplx<T> mk(T a, T b) { cplx<T> r; r.x = a; r.y = b; return r; }
+template <typename T> __device__ __forceinline__ cplx<T> operator+(cplx<T> a, cplx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
+template <typename T> __device__ __forceinline__ cplx<T> operator-(cplx<T> a, cplx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+template <typename T> __device__ __forceinline__ cplx<T> cmul(cplx<T> a, cplx<T> b) {
+    return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <typename T> __device__ __forceinline__ cplx<T> cmulc(cplx<T> a, cplx<T> b) {  // a * conj(b)
+    return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+template <typename T> __device__ __forceinline__ cplx<T> cscale(cplx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
+template <typename T> __device__ __forceinline__ cplx<T> cconj(cplx<T> a) { return mk<T>(a.x, -a.y); }
+// multiply by DIR * i  (i.e. e^{DIR * i pi/2})
+template <int DIR, typename T> __device__ __forceinline__ cplx<T> mul_i(cplx<T> a) {
+    return DIR > 0 ? mk<T>(-a.y, a.x) : mk<T>(a.y, -a.x);
+}
+// multiply by i^q for runtime q in 0..3 (direction already folded into q)
+template <typename T> __device__ __forceinline__ cplx<T> mul_ipow(cplx<T> a, int q) {
+    q &= 3;
+    if (q == 0) return a;
+    if (q == 1) return mk<T>(-a.y, a.x);
+    if (q == 2) return mk<T>(-a.x, -a.y);
+    return mk<T>(a.y, -a.x);
+}
+
+// e^{2 pi i c} for c given in cycles; argument reduced in double so |c| may be large
+// (the defocus phase reaches hundreds of cycles, SURVEY.md section 7 hard part 1).
+__device__ __forceinline__ void cis_cycles(double c, cplx<float>& out) {
+    double f = c - rint(c);            // exact
+    float s, co;
+    sincospif(2.0f * (float)f, &s, &co);
+    out.x = co; out.y = s;
+}
+__device__ __forceinline__ void cis_cycles(double c, cplx<double>& out) {
+    double f = c - rint(c);
+    double s, co;
+    sincospi(2.0 * f, &s, &co);
+    out.x = co; out.y = s;
+}
+
+template <int DIR, typename T> __device__ __forceinline__ void fft2(cplx<T>& a, cplx<T>& b) {
+    cplx<T> t = a - b; a = a + b; b = t;
+}
+
+// radix-4, natural order in/out
+template <int DIR, typename T> __device__ __forceinline__ void fft4(cplx<T>& x0, cplx<T>& x1, cplx<T>& x2, cplx<T>& x3) {
+    cplx<T> s02 = x0 + x2, d02 = x0 - x2, s13 = x1 + x3, d13 = mul_i<DIR>(x1 - x3);
+    x0 = s02 + s13; x2 = s02 - s13; x1 = d02 + d13; x3 = d02 - d13;
+}
+
+// multiply by e^{DIR * 2 pi i * k / 8}, k compile-time
+template <int DIR, int K, typename T> __device__ __forceinline__ cplx<T> mul_w8(cplx<T> a) {
+    constexpr int k = ((K % 8) + 8) % 8;
+    const T h = (T)0.70710678118654752440;
+    if (k == 0) return a;
+    if (k == 2) return mul_i<DIR>(a);
+    if (k == 4) return mk<T>(-a.x, -a.y);
+    if (k == 6) return mul_i<-DIR>(a);
+    if (k == 1) return DIR > 0 ? mk<T>((a.x - a.y) * h, (a.x + a.y) * h) : mk<T>((a.x + a.y) * h, (a.y - a.x) * h);
+    if (k == 3) return DIR > 0 ? mk<T>(-(a.x + a.y) * h, (a.x - a.y) * h) : mk<T>((a.y - a.x) * h, -(a.x + a.y) * h);
+    if (k == 5) return DIR > 0 ? mk<T>((a.y - a.x) * h, -(a.x + a.y) * h) : mk<T>(-(a.x + a.y) * h, (a.x - a.y) * h);
+    /* k == 7 */ return DIR > 0 ? mk<T>((a.x + a.y) * h, (a.y - a.x) * h) : mk<T>((a.x - a.y) * h, (a.x + a.y) * h);
+}
+
+// radix-8 as 2 x radix-4 (decimation in time), natural order in/out
+template <int DIR, typename T> __device__ __forceinline__ void fft8(cplx<T>* x) {
+    // even / odd split
+    cplx<T> e0 = x[0], e1 = x[2], e2 = x[4], e3 = x[6];
+    cplx<T> o0 = x[1], o1 = x[3], o2 = x[5], o3 = x[7];
+    fft4<DIR>(e0, e1, e2, e3);
+    fft4<DIR>(o0, o1, o2, o3);
+    o1 = mul_w8<DIR, 1>(o1); o2 = mul_w8<DIR, 2>(o2); o3 = mul_w8<DIR, 3>(o3);
+    x[0] = e0 + o0; x[4] = e0 - o0;
+    x[1] = e1 + o1; x[5] = e1 - o1;
+    x[2] = e2 + o2; x[6] = e2 - o2;
+    x[3] = e3 + o3; x[7] = e3 - o3;
+}
+
+// multiply by e^{DIR * 2 pi i * k / 16}, k compile-time in 0..15
+template <int DIR, int K, typename T> __device__ __forceinline__ cplx<T> mul_w16(cplx<T> a) {
+    constexpr int k = ((K % 16) + 16) % 16;
+    if (k % 2 == 0) return mul_w8<DIR, k / 2>(a);
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173;
+    // odd k: angle = k * 22.5 deg; (cos, sin) from the k=1 and k=3 pair by symmetry
+    constexpr int q = k / 4;          // quadrant
+    constexpr int r = k % 4;          // 1 or 3
+    T c = (r == 1) ? c1 : s1, s = (r == 1) ? s1 : c1;
+    // rotate by quadrant: (c, s) -> (c,s), (-s,c), (-c,-s), (s,-c)
+    T cc = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
+    T ss = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+    if (DIR < 0) ss = -ss;
+    return mk<T>(a.x * cc - a.y * ss, a.x * ss + a.y * cc);
+}
+
+// radix-16 as 4 x 4, natural order in/out
+template <int DIR, typename T> __device__ __forceinline__ void fft16(cplx<T>* x) {
+    // k = 4a + b ; out = c + 4d
+    cplx<T> t[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        t[b][0] = x[b]; t[b][1] = x[4 + b]; t[b][2] = x[8 + b]; t[b][3] = x[12 + b];
+        fft4<DIR>(t[b][0], t[b][1], t[b][2], t[b][3]);   // over a -> c
+    }
+    // twiddle w16^{b c}
+    t[1][1] = mul_w16<DIR, 1>(t[1][1]); t[1][2] = mul_w16<DIR, 2>(t[1][2]); t[1][3] = mul_w16<DIR, 3>(t[1][3]);
+    t[2][1] = mul_w16<DIR, 2>(t[2][1]); t[2][2] = mul_w16<DIR, 4>(t[2][2]); t[2][3] = mul_w16<DIR, 6>(t[2][3]);
+    t[3][1] = mul_w16<DIR, 3>(t[3][1]); t[3][2] = mul_w16<DIR, 6>(t[3][2]); t[3][3] = mul_w16<DIR, 9>(t[3][3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        fft4<DIR>(t[0][c], t[1][c], t[2][c], t[3][c]);   // over b -> d
+        x[c] = t[0][c]; x[c + 4] = t[1][c]; x[c + 8] = t[2][c]; x[c + 12] = t[3][c];
+    }
+}
+
+template <int DIR, int R, typename T> __device__ __forceinline__ void fft_radix(cplx<T>* x) {
+    static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "radix");
+    if constexpr (R == 2) fft2<DIR>(x[0], x[1]);
+    if constexpr (R == 4) fft4<DIR>(x[0], x[1], x[2], x[3]);
+    if constexpr (R == 8) fft8<DIR>(x);
+    if constexpr (R == 16) fft16<DIR>(x);
+}
+
+}  // namespace pyotf

@@ -1,0 +1,114 @@
+"""K1 parity (GPU): fused pupil -> defocus -> 2D IFFT -> |.|^2 against the CPU oracle and the
+golden vectors generated from the live reference.  All calls go through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "fp64": 1e-11}
+
+
+def _run(precision, wl, na, ni, res, size, zrange, vec_corr="none", condition="sine", pupil=None,
+         want_psfa=True):
+    import torch
+
+    from pyotf_b200 import _engine as eng
+
+    support = -1
+    pupilc = None
+    if pupil is not None:
+        pd = eng.to_device_c128(pupil)
+        support = eng.pupil_support(pd)
+    h = eng.hanser_handle(wl, na, ni, res, size, vec_corr, condition, precision, support)
+    if pupil is not None:
+        pupilc = h.pack_pupil(pd[None])
+    z = eng.to_device_f64(np.atleast_1d(zrange))
+    psfa, psfi = h.psf(z, pupilc, want_psfa=want_psfa, want_psfi=True)
+    torch.cuda.synchronize()
+    return (psfa[0].cpu().numpy() if psfa is not None else None), psfi[0].cpu().numpy()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("vec_corr", ["none", "x", "y", "z", "total"])
+@pytest.mark.parametrize("condition", ["none", "sine", "herschel"])
+def test_small_all_modes_vs_oracle_and_golden(precision, vec_corr, condition):
+    from oracle import pyotf_oracle as orc
+
+    g = np.load(os.path.join(GOLDEN, "hanser_small.npz"))
+    wl, na, ni, res, size, zres, zsize = g["params"]
+    size, zsize = int(size), int(zsize)
+    z = orc.default_zrange(zsize, zres)
+    psfa, psfi = _run(precision, wl, na, ni, res, size, z, vec_corr, condition)
+    ref_a = orc.hanser_psfa(wl, na, ni, res, size, z, vec_corr, condition)
+    assert psfa.shape == ref_a.shape
+    assert rel_l2(psfa, ref_a) <= TOL[precision]
+    assert rel_l2(psfi, orc.psfi(ref_a)) <= TOL[precision]
+    assert rel_l2(psfi, g[f"psfi_{vec_corr}_{condition}"]) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("size", [32, 64, 128, 256])
+def test_sizes_and_user_pupil(precision, size):
+    from oracle import pyotf_oracle as orc
+
+    rng = np.random.default_rng(size)
+    wl, na, ni, res = 520, 0.85, 1.0, 130
+    z = np.array([-2150.0, -300.0, 0.0, 777.7, 4100.0])
+    _, kr, _, _, _ = orc.hanser_kspace(wl, ni, res, size)
+    # masked random pupil (phase-retrieval like)
+    pupil = orc.hanser_pupil(kr, na, wl) * (1 + 0.3 * rng.standard_normal((size, size))) * np.exp(
+        1j * rng.standard_normal((size, size)))
+    psfa, psfi = _run(precision, wl, na, ni, res, size, z, "none", "none", pupil)
+    ref_a = orc.hanser_psfa(wl, na, ni, res, size, z, "none", "none", pupil)
+    assert rel_l2(psfa, ref_a) <= TOL[precision]
+    assert rel_l2(psfi, orc.psfi(ref_a)) <= TOL[precision]
+    # dense random pupil (support = whole grid)
+    pupil = rng.standard_normal((size, size)) + 1j * rng.standard_normal((size, size))
+    psfa, psfi = _run(precision, wl, na, ni, res, size, z[:2], "none", "sine", pupil)
+    ref_a = orc.hanser_psfa(wl, na, ni, res, size, z[:2], "none", "sine", pupil)
+    assert rel_l2(psfa, ref_a) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_cfg1_golden(precision):
+    """BASELINE config 1: HanserPSF(520, 0.85, 1.0, 130, 256, zres=300, zsize=128) -> PSFi."""
+    g = np.load(os.path.join(GOLDEN, "cfg1_hanser256.npz"))
+    _, psfi = _run(precision, 520, 0.85, 1.0, 130, 256, g["zrange"], want_psfa=False)
+    tol = TOL[precision]
+    assert psfi.shape == (128, 256, 256)
+    assert rel_l2(psfi.sum((1, 2)), g["psfi_plane_sums"]) <= tol
+    assert rel_l2(psfi[g["psfi_plane_idx"]], g["psfi_planes"]) <= tol
+    for i, p in zip(g["psfi_plane_idx"], g["psfi_planes"]):
+        assert rel_l2(psfi[i], p) <= tol, f"plane {i}"
+    assert rel_l2(psfi[:, 128, 128], g["psfi_center_line"]) <= tol
+    assert abs(np.linalg.norm(psfi.ravel().astype(np.float64)) / g["psfi_l2"] - 1) <= tol
+    # known-answer values from SURVEY.md section 8c
+    assert abs(psfi.astype(np.float64).sum() / 23.75643331623896 - 1) <= tol
+    assert abs(psfi[64, 128, 128] / 0.02609296492831893 - 1) <= 10 * tol
+    assert (psfi >= 0).all()
+
+
+def test_geometry_tables_match_oracle():
+    """The fp64 edge predicate kr <= na/wl and kz must match numpy's bit for bit / to 1 ulp."""
+    from oracle import pyotf_oracle as orc
+    from pyotf_b200 import _engine as eng
+
+    for (wl, na, ni, res, size) in [(520, 0.85, 1.0, 130, 256), (525, 1.27, 1.33, 100, 128),
+                                    (488, 1.4, 1.518, 65, 256), (500, 0.5, 1.0, 250, 64)]:
+        h = eng.hanser_handle(wl, na, ni, res, size, "none", "sine", "fp64", -1)
+        kz, amp, mask = [t.cpu().numpy() for t in h.tables()]
+        _, kr, _, kmag, kz_ref = orc.hanser_kspace(wl, ni, res, size)
+        sel = np.arange(h.f0, h.f0 + h.K) % size
+        sub = np.ix_(sel, sel)
+        np.testing.assert_array_equal(mask.astype(bool), (kr <= na / wl)[sub])
+        # nothing of the ideal pupil lies outside the compact box
+        assert (kr <= na / wl).sum() == mask.sum()
+        # hypot is within 1 ulp of glibc's; kz = sqrt(kmag^2 - kr^2) amplifies that near kr -> kmag
+        np.testing.assert_allclose(kz, kz_ref[sub], rtol=1e-13, atol=8 * np.finfo(float).eps * kmag)
+        theta = np.arcsin((kr < kmag) * kr / kmag)
+        a = (1 / np.sqrt(np.cos(theta))) * (kr <= na / wl)
+        np.testing.assert_allclose(amp[0], a[sub], rtol=1e-14)
