@@ -44,6 +44,8 @@ typedef struct pyotf_hanser_params {
     int dtype;              /* PYOTF_F32 / PYOTF_F64                                  */
     int support;            /* -1: no user pupil, ideal mask kr <= na/wl is applied
                                (HanserPSF._gen_pupil, otf.py:346-355);
+                               -2: a pupil is supplied that lives on the ideal pupil's box
+                               (phase retrieval, apply_aberration);
                                h >= 0: a user pupil is supplied whose non-zero support is
                                |f| <= h frequency bins (see pyotf_b200_pupil_support)    */
 } pyotf_hanser_params;
@@ -79,6 +81,42 @@ int pyotf_b200_hanser_pack_pupil(const pyotf_hanser_t* h, const void* pupil_c128
 int pyotf_b200_hanser_psf(const pyotf_hanser_t* h, const double* z_dev, int nz, const void* pupilc_dev,
                           int batch, long long pupil_stride, void* psfa_out_dev, void* psfi_out_dev,
                           void* stream);
+
+/* Full-grid pupil coordinates for the API hooks (HanserPSF._gen_kr, otf.py:335-344):
+ * kr, phi, kz as [size*size] float64, unshifted; any output may be NULL. */
+int pyotf_b200_hanser_kspace(double wl, double ni, double res, int size, double* kr_dev, double* phi_dev,
+                             double* kz_dev, void* stream);
+/* exp(2 pi i kz z) -> [nz][npix] complex128 (HanserPSF._calc_defocus, otf.py:357-360). */
+int pyotf_b200_hanser_defocus(const double* kz_dev, long long npix, const double* z_dev, int nz, void* out_c128_dev,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Zernike polynomials  (pyotf/zernike.py:251-365) and apply_aberration (otf.py:595-645)
+ * ---------------------------------------------------------------------------------- */
+/* out[mode][pt] = Z_{n[mode]}^{m[mode]}(r[pt], theta[pt]), float64; zero for r > 1. */
+int pyotf_b200_zernike(const double* r_dev, const double* theta_dev, long long npts, const int* n_dev,
+                       const int* m_dev, int nmodes, int norm, double* out_dev, void* stream);
+/* Batched aberrated pupils in the handle's compact layout / dtype:
+ *   pupil_b = (sum_j mcoefs[b][j] Z_j + |ideal pupil|) * exp(i sum_j pcoefs[b][j] Z_j)
+ * with Z_j evaluated at r = kr*wl/na, theta = phi (otf.py:626-642).  n_dev/m_dev are the
+ * (n, m) degrees of the nmodes modes (Noll order for apply_aberration); mcoefs/pcoefs are
+ * [batch][nmodes] float64, either may be NULL.  The handle must have support == -2. */
+int pyotf_b200_hanser_aberration_pupil(const pyotf_hanser_t* h, const int* n_dev, const int* m_dev, int nmodes,
+                                       const double* mcoefs_dev, const double* pcoefs_dev, int batch,
+                                       void* pupilc_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Shifted N-d FFT  (pyotf/utils.py:15-22; OTFi otf.py:209-212; OTFa otf.py:435-438, 589-592)
+ * ---------------------------------------------------------------------------------- */
+/* out = [fftshift](fftn)([ifftshift] in) over `axes` (forward), or
+ * out = [ifftshift](ifftn)([fftshift] in) (inverse; numpy "backward" 1/n normalisation).
+ * `in` is a C-contiguous array of `ndim` <= 8 dims, real (real_in = 1) or complex; `out` is
+ * complex with the same shape and may alias `in` only when `in` is complex.  shift_in /
+ * shift_out = 1 give easy_fft / easy_ifft; 0/0 is the plain transform. */
+int pyotf_b200_fftn(const void* in_dev, void* out_dev, int ndim, const long long* shape, const int* axes, int naxes,
+                    int inverse, int real_in, int shift_in, int shift_out, int dtype, void* stream);
+/* out[i] = sum_v |a[v][i]|^2  (BasePSF.PSFi from an existing PSFa, otf.py:204-207) */
+int pyotf_b200_abs2_sum0(const void* a_dev, int nvec, long long n, void* out_dev, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -147,3 +147,54 @@ def to_device_f64(a):
 def to_device_c128(a):
     torch = _torch()
     return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.complex128)), device="cuda")
+
+
+def to_device_i32(a):
+    torch = _torch()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.int32)), device="cuda")
+
+
+def zernike_eval(r, theta, n, m, norm):
+    """Host arrays in, host [nmodes, npts] float64 out; evaluated by the CUDA kernel."""
+    torch = _torch()
+    rd, td = to_device_f64(np.ravel(r)), to_device_f64(np.ravel(theta))
+    nd, md = to_device_i32(n), to_device_i32(m)
+    npts, nmodes = rd.numel(), nd.numel()
+    out = torch.empty((nmodes, npts), dtype=torch.float64, device="cuda")
+    if npts and nmodes:
+        _lib.check(_lib.load().pyotf_b200_zernike(ptr(rd), ptr(td), npts, ptr(nd), ptr(md), nmodes, int(norm),
+                                                  ptr(out), stream_ptr()))
+    return out.cpu().numpy()
+
+
+def hanser_kspace(wl, ni, res, size):
+    """(kr, phi, kz) float64 [N, N] device tensors, unshifted (HanserPSF._gen_kr)."""
+    torch = _torch()
+    kr, phi, kz = (torch.empty((size, size), dtype=torch.float64, device="cuda") for _ in range(3))
+    _lib.check(_lib.load().pyotf_b200_hanser_kspace(float(wl), float(ni), float(res), int(size), ptr(kr), ptr(phi),
+                                                    ptr(kz), stream_ptr()))
+    return kr, phi, kz
+
+
+def hanser_defocus(kz_dev, z_dev):
+    torch = _torch()
+    nz, npix = int(z_dev.numel()), int(kz_dev.numel())
+    out = torch.empty((nz,) + tuple(kz_dev.shape), dtype=torch.complex128, device="cuda")
+    _lib.check(_lib.load().pyotf_b200_hanser_defocus(ptr(kz_dev), npix, ptr(z_dev), nz, ptr(out), stream_ptr()))
+    return out
+
+
+def aberration_pupil(handle, n, m, mcoefs, pcoefs):
+    """Compact pupils [B, K, K] for [B, nmodes] coefficient arrays (either may be None)."""
+    torch = _torch()
+    _, ct = torch_dtypes(handle.precision)
+    ref = mcoefs if mcoefs is not None else pcoefs
+    ref = np.atleast_2d(np.asarray(ref, dtype=np.float64))
+    B, nmodes = ref.shape
+    mc = to_device_f64(np.atleast_2d(mcoefs)) if mcoefs is not None else None
+    pc = to_device_f64(np.atleast_2d(pcoefs)) if pcoefs is not None else None
+    nd, md = to_device_i32(n), to_device_i32(m)
+    out = torch.empty((B, handle.K, handle.K), dtype=ct, device="cuda")
+    _lib.check(_lib.load().pyotf_b200_hanser_aberration_pupil(handle._h, ptr(nd), ptr(md), nmodes, ptr(mc), ptr(pc), B,
+                                                              ptr(out), stream_ptr()))
+    return out

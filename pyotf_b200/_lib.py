@@ -24,7 +24,7 @@ class Pyotf_b200Error(RuntimeError):
 
 _lib = None
 
-_vp, _i, _ll, _ip = C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_int)
+_vp, _i, _ll, _ip, _d = C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_int), C.c_double
 
 # name -> (restype, argtypes); every symbol include/pyotf_b200.h declares
 PROTOTYPES = {
@@ -38,6 +38,12 @@ PROTOTYPES = {
     "pyotf_b200_pupil_support": (_i, [_vp, _i, _ip, _vp]),
     "pyotf_b200_hanser_pack_pupil": (_i, [_vp, _vp, _i, _vp, _vp]),
     "pyotf_b200_hanser_psf": (_i, [_vp, _vp, _i, _vp, _i, _ll, _vp, _vp, _vp]),
+    "pyotf_b200_hanser_kspace": (_i, [_d, _d, _d, _i, _vp, _vp, _vp, _vp]),
+    "pyotf_b200_hanser_defocus": (_i, [_vp, _ll, _vp, _i, _vp, _vp]),
+    "pyotf_b200_zernike": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _vp, _vp]),
+    "pyotf_b200_fftn": (_i, [_vp, _vp, _i, C.POINTER(_ll), _ip, _i, _i, _i, _i, _i, _i, _vp]),
+    "pyotf_b200_abs2_sum0": (_i, [_vp, _i, _ll, _vp, _i, _vp]),
+    "pyotf_b200_hanser_aberration_pupil": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
 }
 
 

@@ -1,6 +1,7 @@
 // extern "C" boundary: argument validation, handle lifetime, dtype dispatch.
 #include "common.cuh"
 #include "hanser.cuh"
+#include "zernike.cuh"
 
 namespace pyotf {
 static thread_local std::string g_last_error;
@@ -8,6 +9,26 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 }  // namespace pyotf
 
 using namespace pyotf;
+
+template <typename T>
+static int aberration_launch(const pyotf_hanser* h, const int* n, const int* m, int nmodes, const double* mc,
+                             const double* pc, int batch, void* out, cudaStream_t s) {
+    constexpr int PIX = 64;
+    AberrationParams p;
+    p.N = h->N; p.K = h->K; p.f0 = h->f0; p.nmodes = nmodes; p.batch = batch;
+    p.has_mag = mc != nullptr; p.has_phase = pc != nullptr;
+    p.kstep = 1.0 / ((double)h->N * h->p.res); p.wl = h->p.wl; p.na = h->p.na; p.diff_limit = h->p.na / h->p.wl;
+    size_t smem = sizeof(double) * ((size_t)nmodes * PIX + PIX);
+    auto kern = aberration_pupil_kernel<T, PIX>;
+    PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int KK = h->K * h->K;
+    int gy = batch >= 256 ? 4 : 1;
+    dim3 grid((unsigned)((KK + PIX - 1) / PIX), (unsigned)gy);
+    kern<<<grid, 256, smem, s>>>(p, n, m, mc, pc, (cplx<T>*)out);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 
 extern "C" {
 
@@ -34,6 +55,7 @@ int pyotf_b200_hanser_create(const pyotf_hanser_params* p, void* stream, pyotf_h
     h->p = *p;
     h->N = p->size;
     PYOTF_CUDA_OK(cudaGetDevice(&h->device));
+    PYOTF_REQUIRE(p->support >= -2, "hanser_create: bad support");
     int H;
     if (p->support < 0) {
         // conservative bound on the ideal pupil radius in bins: kr <= na/wl, k = f / (N res)
@@ -113,13 +135,74 @@ int pyotf_b200_hanser_psf(const pyotf_hanser_t* h, const double* z_dev, int nz, 
     PYOTF_REQUIRE(h && z_dev, "hanser_psf: null argument");
     PYOTF_REQUIRE(nz > 0 && batch > 0, "hanser_psf: nz and batch must be positive");
     PYOTF_REQUIRE(psfa_out_dev || psfi_out_dev, "hanser_psf: no output requested");
-    PYOTF_REQUIRE((h->p.support < 0) == (pupilc_dev == nullptr),
+    PYOTF_REQUIRE((h->p.support == -1) == (pupilc_dev == nullptr),
                   "hanser_psf: handle support mode and pupil argument disagree");
     PYOTF_REQUIRE(batch <= 65535, "hanser_psf: batch too large for one launch");
     cudaStream_t s = (cudaStream_t)stream;
     return h->p.dtype == PYOTF_F32
                ? hanser_launch<float>(h, z_dev, nz, pupilc_dev, batch, pupil_stride, psfa_out_dev, psfi_out_dev, s)
                : hanser_launch<double>(h, z_dev, nz, pupilc_dev, batch, pupil_stride, psfa_out_dev, psfi_out_dev, s);
+}
+
+int pyotf_b200_hanser_kspace(double wl, double ni, double res, int size, double* kr, double* phi, double* kz,
+                             void* stream) {
+    PYOTF_REQUIRE(size > 0 && wl > 0 && res > 0, "hanser_kspace: bad argument");
+    int n = size * size;
+    hanser_kspace_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(size, 1.0 / ((double)size * res), ni / wl,
+                                                                           kr, phi, kz);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pyotf_b200_hanser_defocus(const double* kz, long long npix, const double* z, int nz, void* out, void* stream) {
+    PYOTF_REQUIRE(kz && z && out && npix > 0 && nz > 0 && nz <= 65535, "hanser_defocus: bad argument");
+    dim3 grid((unsigned)((npix + 255) / 256), (unsigned)nz);
+    hanser_defocus_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((int)npix, kz, z, nz, (double2*)out);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pyotf_b200_zernike(const double* r, const double* theta, long long npts, const int* n, const int* m, int nmodes,
+                       int norm, double* out, void* stream) {
+    PYOTF_REQUIRE(r && theta && n && m && out && npts > 0 && nmodes > 0, "zernike: bad argument");
+    zernike_eval_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, (cudaStream_t)stream>>>(r, theta, npts, n, m, nmodes,
+                                                                                         norm, out);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pyotf_b200_hanser_aberration_pupil(const pyotf_hanser_t* h, const int* n, const int* m, int nmodes,
+                                       const double* mc, const double* pc, int batch, void* out, void* stream) {
+    PYOTF_REQUIRE(h && n && m && out, "aberration_pupil: null argument");
+    PYOTF_REQUIRE(h->p.support == -2, "aberration_pupil: handle must be created with support == -2");
+    PYOTF_REQUIRE(nmodes > 0 && nmodes <= 400 && batch > 0, "aberration_pupil: bad nmodes/batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    return h->p.dtype == PYOTF_F32 ? aberration_launch<float>(h, n, m, nmodes, mc, pc, batch, out, s)
+                                   : aberration_launch<double>(h, n, m, nmodes, mc, pc, batch, out, s);
+}
+
+int pyotf_b200_fftn(const void* in, void* out, int ndim, const long long* shape, const int* axes, int naxes, int inverse,
+                    int real_in, int shift_in, int shift_out, int dtype, void* stream) {
+    PYOTF_REQUIRE(in && out && shape && axes, "fftn: null argument");
+    PYOTF_REQUIRE(ndim >= 1 && ndim <= 8 && naxes >= 1 && naxes <= ndim, "fftn: bad ndim / naxes");
+    PYOTF_REQUIRE(dtype == PYOTF_F32 || dtype == PYOTF_F64, "fftn: bad dtype");
+    PYOTF_REQUIRE(!(real_in && in == out), "fftn: real input cannot be transformed in place");
+    unsigned seen = 0;
+    for (int k = 0; k < naxes; ++k) {
+        PYOTF_REQUIRE(axes[k] >= 0 && axes[k] < ndim && !(seen & (1u << axes[k])), "fftn: bad axes");
+        seen |= 1u << axes[k];
+    }
+    for (int d = 0; d < ndim; ++d) PYOTF_REQUIRE(shape[d] > 0, "fftn: empty dimension");
+    cudaStream_t s = (cudaStream_t)stream;
+    return dtype == PYOTF_F32
+               ? fftn_run<float>(in, out, ndim, shape, axes, naxes, inverse, real_in, shift_in, shift_out, s)
+               : fftn_run<double>(in, out, ndim, shape, axes, naxes, inverse, real_in, shift_in, shift_out, s);
+}
+
+int pyotf_b200_abs2_sum0(const void* a, int nvec, long long n, void* out, int dtype, void* stream) {
+    PYOTF_REQUIRE(a && out && nvec > 0 && n > 0, "abs2_sum0: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    return dtype == PYOTF_F32 ? abs2_sum0_run<float>(a, nvec, n, out, s) : abs2_sum0_run<double>(a, nvec, n, out, s);
 }
 
 }  // extern "C"

@@ -48,4 +48,8 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
                   long long pupil_stride, void* psfa, void* psfi, cudaStream_t s);
 template <typename T>
 int hanser_pack(const pyotf_hanser* h, const void* src, int batch, void* dst, cudaStream_t s);
+template <typename T>
+int fftn_run(const void* in, void* out, int ndim, const long long* shape, const int* axes, int naxes, int inverse,
+             int real_in, int shift_in, int shift_out, cudaStream_t s);
+template <typename T> int abs2_sum0_run(const void* a, int nvec, long long n, void* out, cudaStream_t s);
 }  // namespace pyotf

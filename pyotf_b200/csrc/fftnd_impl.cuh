@@ -1,0 +1,87 @@
+// Host launchers for the axis-pass FFT (instantiated per dtype in fftnd_f32.cu / fftnd_f64.cu).
+#pragma once
+#include "common.cuh"
+#include "fftnd.cuh"
+
+namespace pyotf {
+
+template <int DIR, typename TIN, typename T, int L, bool POW2, int TI>
+int fft_axis_launch_ti(const AxisPass& p, const void* src, void* dst, size_t smem, cudaStream_t s) {
+    auto kern = fft_axis_kernel<DIR, TIN, T, L, TI, POW2>;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    long long nblocks = p.n_inner == 1 ? (p.n_outer + TI - 1) / TI : p.n_outer * ((p.n_inner + TI - 1) / TI);
+    PYOTF_REQUIRE(nblocks > 0 && nblocks < (1ll << 31), "fft: bad grid");
+    kern<<<(unsigned)nblocks, 256, smem, s>>>(p, (const TIN*)src, (cplx<T>*)dst);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int DIR, typename TIN, typename T, int L, bool POW2>
+int fft_axis_launch_l(const AxisPass& p, const void* src, void* dst, int smem_limit, cudaStream_t s) {
+    // lines per tile: 16 keeps 128 B (fp32) / 256 B (fp64) global segments on strided axes;
+    // long axes drop to 8 / 4 lines so the tile still fits (and two CTAs share an SM when possible)
+    const int Lr = POW2 ? L : p.L;
+    auto need = [&](int ti) { return sizeof(cplx<T>) * ((size_t)Lr + (size_t)ti * (Lr + 1) * (POW2 ? 1 : 2)); };
+    const size_t soft = (size_t)smem_limit / 2 - 1024;
+    if (need(16) <= soft || (need(8) > (size_t)smem_limit && need(16) <= (size_t)smem_limit))
+        return fft_axis_launch_ti<DIR, TIN, T, L, POW2, 16>(p, src, dst, need(16), s);
+    if (need(8) <= soft || (need(4) > (size_t)smem_limit && need(8) <= (size_t)smem_limit))
+        return fft_axis_launch_ti<DIR, TIN, T, L, POW2, 8>(p, src, dst, need(8), s);
+    PYOTF_REQUIRE(need(4) <= (size_t)smem_limit, "fft: axis too long for the shared-memory staged pass");
+    return fft_axis_launch_ti<DIR, TIN, T, L, POW2, 4>(p, src, dst, need(4), s);
+}
+
+template <int DIR, typename TIN, typename T>
+int fft_axis_launch(const AxisPass& p, const void* src, void* dst, int smem_limit, cudaStream_t s) {
+    switch (p.L) {
+#define PYOTF_CASE(LL) case LL: return fft_axis_launch_l<DIR, TIN, T, LL, true>(p, src, dst, smem_limit, s);
+        PYOTF_CASE(2) PYOTF_CASE(4) PYOTF_CASE(8) PYOTF_CASE(16) PYOTF_CASE(32) PYOTF_CASE(64) PYOTF_CASE(128)
+        PYOTF_CASE(256) PYOTF_CASE(512) PYOTF_CASE(1024) PYOTF_CASE(2048)
+#undef PYOTF_CASE
+        default: return fft_axis_launch_l<DIR, TIN, T, 0, false>(p, src, dst, smem_limit, s);
+    }
+}
+
+// out = [shift](fftn / ifftn)([shift] in) over `axes` of a C-contiguous array
+template <typename T>
+int fftn_run(const void* in, void* out, int ndim, const long long* shape, const int* axes, int naxes, int inverse,
+             int real_in, int shift_in, int shift_out, cudaStream_t s) {
+    int dev = 0, smem_limit = 0;
+    PYOTF_CUDA_OK(cudaGetDevice(&dev));
+    PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    bool first = true;
+    // contiguous axis last-to-first keeps the real->complex pass on the fastest axis when present
+    for (int k = naxes - 1; k >= 0; --k) {
+        int ax = axes[k];
+        AxisPass p;
+        p.L = (int)shape[ax];
+        p.n_outer = 1; p.n_inner = 1;
+        for (int d = 0; d < ax; ++d) p.n_outer *= shape[d];
+        for (int d = ax + 1; d < ndim; ++d) p.n_inner *= shape[d];
+        int half = p.L / 2, rest = (p.L - half) % p.L;
+        p.in_shift = shift_in ? (inverse ? rest : half) : 0;
+        p.out_shift = shift_out ? (inverse ? rest : half) : 0;
+        p.scale = inverse ? 1.0 / (double)p.L : 1.0;
+        const void* src = first ? in : out;
+        int rc;
+        if (first && real_in) rc = inverse ? fft_axis_launch<1, T, T>(p, src, out, smem_limit, s)
+                                           : fft_axis_launch<-1, T, T>(p, src, out, smem_limit, s);
+        else rc = inverse ? fft_axis_launch<1, cplx<T>, T>(p, src, out, smem_limit, s)
+                          : fft_axis_launch<-1, cplx<T>, T>(p, src, out, smem_limit, s);
+        if (rc) return rc;
+        first = false;
+    }
+    return 0;
+}
+
+template <typename T> int abs2_sum0_run(const void* a, int nvec, long long n, void* out, cudaStream_t s) {
+    abs2_sum0_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const cplx<T>*)a, nvec, (size_t)n, (T*)out);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pyotf
