@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the PSF/OTF hot path on B200 (driver contract: see README / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload hanser256|pr|library|sheppard] [--precision fp32|fp64]
+
+Default workload = BASELINE.json config 1, the one the metric "HanserPSF z-planes/s at 256^2"
+is quoted on: HanserPSF(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=256, zsize=128) -> PSFi.
+One step = one pass of K1 over that 128-plane stack (one kernel launch per GPU).  With N GPUs
+every rank owns its own contiguous 128-plane block of a 128*N-plane stack (weak scaling, no
+data-path collective).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG1 = dict(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=256, zsize=128)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arms (the ONLY place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------
+def _cpu_hanser_chunk(args):
+    from oracle import pyotf_oracle as orc
+
+    kw, z = args
+    a = orc.hanser_psfa(kw["wl"], kw["na"], kw["ni"], kw["res"], kw["size"], z)
+    return float(orc.psfi(a).sum())
+
+
+def cpu_baseline_hanser(budget_s=12.0):
+    """Oracle port (numpy, single thread) on the full cfg1 stack, repeated for ~budget_s."""
+    from oracle import pyotf_oracle as orc
+
+    z = orc.default_zrange(CFG1["zsize"], CFG1["zres"])
+    _cpu_hanser_chunk((CFG1, z))  # warm-up
+    reps, t0 = 0, time.perf_counter()
+    best = None
+    while True:
+        t = time.perf_counter()
+        _cpu_hanser_chunk((CFG1, z))
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= 30:
+            break
+    total = time.perf_counter() - t0
+    return {"value": CFG1["zsize"] * reps / total, "unit": "planes/s", "cores": 1, "kind": "port",
+            "sample": f"oracle/pyotf_oracle.py (numpy/pocketfft, complex128) on the full cfg1 stack "
+                      f"(128 planes of 256^2), {reps} repetitions in {total:.1f} s; best single = "
+                      f"{CFG1['zsize'] / best:.1f} planes/s; {os.cpu_count()} cores available, 1 used"}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port) using every host core:
+    the stack is z-chunked over a process pool (HanserPSF(zrange=chunk) is the reference's own shard API)."""
+    import multiprocessing as mp
+
+    from oracle import pyotf_oracle as orc
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = max(1, min(os.cpu_count() or 1, 32))
+    z = orc.default_zrange(CFG1["zsize"], CFG1["zres"])
+    chunks = [c for c in np.array_split(z, ncores) if len(c)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(chunks)) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_hanser_chunk, [(CFG1, c) for c in chunks])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_hanser_chunk, [(CFG1, c) for c in chunks])
+        dt = time.perf_counter() - t0
+    value = CFG1["zsize"] * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "HanserPSF z-planes/s at 256^2", "value": value, "unit": "planes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "hanser256: HanserPSF 256^2 x 128 planes (BASELINE config 1) -> PSFi, CPU",
+                   "step": "one 128-plane stack, z-chunked over a process pool"},
+        "cpu_baseline": {"value": value, "unit": "planes/s", "cores": len(chunks), "kind": "port",
+                         "sample": f"oracle port (numpy complex128), full cfg1 stack per step over {len(chunks)} "
+                                   f"processes"},
+        "e2e": {"value": value, "unit": "planes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from pyotf_b200 import _engine as eng
+    from pyotf_b200 import _lib
+    from pyotf_b200.otf import HanserPSF
+
+    precision = args.precision
+    rt = torch.float32 if precision == "fp32" else torch.float64
+    esize = 4 if precision == "fp32" else 8
+    N, nz = CFG1["size"], CFG1["zsize"]
+    # weak scaling: rank r owns planes [r*nz, (r+1)*nz) of an nz*world-plane stack
+    zall = (np.arange(nz * world) - (nz * world + 1) // 2) * CFG1["zres"]
+    zr = zall[rank * nz:(rank + 1) * nz].astype(np.float64)
+    h = eng.hanser_handle(CFG1["wl"], CFG1["na"], CFG1["ni"], CFG1["res"], N, "none", "sine", precision, -1)
+    zd = eng.to_device_f64(zr)
+    ring = 8  # 8 x 32 MiB (fp32) outputs = 256 MiB > 126 MB L2: every step's stores must reach HBM
+    outs = [torch.empty((1, nz, N, N), dtype=rt, device="cuda") for _ in range(ring)]
+    lib = _lib.load()
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    calls = [(h._h, C.c_void_p(zd.data_ptr()), nz, C.c_void_p(0), 1, 0, C.c_void_p(0), C.c_void_p(o.data_ptr()), sp)
+             for o in outs]
+
+    def step(i):
+        rc = lib.pyotf_b200_hanser_psf(*calls[i % ring])
+        if rc:
+            _lib.check(rc)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # keep the GPU busy long enough for nvidia-smi to see clocks under load: repeat the K-step
+    # measurement until >= 0.5 s of device time, report the best repetition (each is exactly K steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps, best_ms, t_wall = 0, None, time.perf_counter()
+    while True:
+        barrier()
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        best_ms = ms if best_ms is None else min(best_ms, ms)
+        reps += 1
+        if time.perf_counter() - t_wall > args.min_seconds or reps >= 200:
+            break
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = best_ms / args.steps
+    planes_per_s = nz * world / (ms_per_step * 1e-3)
+
+    # ---- e2e through the public API: host zrange in, host PSFi (numpy) out, every step ----
+    model = HanserPSF(precision=precision, **CFG1)
+    z_host = torch.from_numpy(zr.copy()).pin_memory()
+    for _ in range(2):
+        model.zrange = z_host.numpy()
+        _ = model.PSFi
+    barrier()
+    ksteps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(ksteps):
+        model.zrange = z_host.numpy()
+        p = model.PSFi
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / ksteps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert p.shape == (nz, N, N)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        alg_bytes = nz * N * N * esize  # N^2 * s_r per plane -> PSFi only
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+                traffic = json.load(f).get(precision)
+        except Exception:
+            pass
+        line = {
+            "metric": "HanserPSF z-planes/s at 256^2", "value": planes_per_s, "unit": "planes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if precision == "fp32" else "f64", "data": "synthetic",
+            "config": {"workload": "hanser256: HanserPSF(wl=520,na=0.85,ni=1.0,res=130,zres=300,size=256,"
+                                   "zsize=128) -> PSFi (BASELINE config 1)",
+                       "step": "one fused K1 launch over the 128-plane stack per GPU",
+                       "l2": "outputs rotate over 8 x 32 MiB buffers (256 MiB > 126 MB L2)",
+                       "timing": f"best of {reps} repetitions of exactly {args.steps} steps, CUDA events on the "
+                                 f"launch stream, max over ranks",
+                       "parallelism": f"z-shard x{world} (no collective)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "hanser_psf_kernel", "algorithmic_bytes_per_launch": alg_bytes},
+            "clocks": clocks,
+            "e2e": {"value": nz * world / e2e_s, "unit": "planes/s", "h2d_bytes_per_step": int(zr.nbytes),
+                    "d2h_bytes_per_step": int(nz * N * N * esize), "ms_per_step": 1e3 * e2e_s,
+                    "path": "HanserPSF.zrange = host array; HanserPSF.PSFi -> numpy (pinned D2H)"},
+            "gpu_launches": args.steps,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_hanser()
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hanser256")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="repeat the K-step measurement for at least this long (clock sampling); 0 = once")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -56,10 +56,11 @@ typedef struct pyotf_hanser pyotf_hanser_t;
  * otf.py:335-344, and the z-independent factors of _gen_psf, otf.py:392-417). */
 int pyotf_b200_hanser_create(const pyotf_hanser_params* params, void* stream, pyotf_hanser_t** out);
 int pyotf_b200_hanser_destroy(pyotf_hanser_t* h);
-/* K = edge of the compact support box, f0 = its first frequency bin, nvec = 1|2|6 */
-int pyotf_b200_hanser_info(const pyotf_hanser_t* h, int* K, int* f0, int* nvec);
-/* copies the geometry tables out (any pointer may be NULL): kz [K*K] f64, amp [nvec*K*K] in
- * the handle's dtype, mask [K*K] u8 -- used by the parity tests for the edge predicates */
+/* K = edge of the compact support box, rows = allocated rows of every compact table / pupil
+ * (K + zero padding: compact arrays are [rows][K]), f0 = first frequency bin, nvec = 1|2|6 */
+int pyotf_b200_hanser_info(const pyotf_hanser_t* h, int* K, int* rows, int* f0, int* nvec);
+/* copies the geometry tables out (any pointer may be NULL): kz [rows*K] f64, amp [nvec*rows*K]
+ * in the handle's dtype, mask [rows*K] u8 -- used by the parity tests for the edge predicates */
 int pyotf_b200_hanser_tables(const pyotf_hanser_t* h, double* kz_dev, void* amp_dev, unsigned char* mask_dev,
                              void* stream);
 
@@ -68,14 +69,14 @@ int pyotf_b200_hanser_tables(const pyotf_hanser_t* h, double* kz_dev, void* amp_
 int pyotf_b200_pupil_support(const void* pupil_c128_dev, int size, int* hmax_host, void* stream);
 
 /* Gathers `batch` unshifted size x size complex128 pupils into the handle's compact centred
- * K x K layout and dtype (the `pupil_base` argument of _gen_psf, otf.py:362-389). */
+ * [rows][K] layout and dtype (the `pupil_base` argument of _gen_psf, otf.py:362-389). */
 int pyotf_b200_hanser_pack_pupil(const pyotf_hanser_t* h, const void* pupil_c128_dev, int batch,
                                  void* pupilc_out_dev, void* stream);
 
 /* K1 -- HanserPSF._gen_psf + BasePSF.PSFi  (otf.py:362-428, 204-207).
  *   z_dev        [nz] float64 plane positions (HanserPSF.zrange, otf.py:296-333)
  *   pupilc_dev   NULL (ideal pupil) or [batch] compact pupils, `pupil_stride` elements apart
- *                (0 = one pupil shared by the whole batch)
+ *                (0 = one pupil shared by the whole batch; rows*K for a dense batch)
  *   psfa_out_dev NULL or [batch][nvec][nz][N][N] complex, spatially shifted
  *   psfi_out_dev NULL or [batch][nz][N][N] real, spatially shifted                         */
 int pyotf_b200_hanser_psf(const pyotf_hanser_t* h, const double* z_dev, int nz, const void* pupilc_dev,

@@ -63,9 +63,9 @@ class HanserHandle:
         h = C.c_void_p()
         _lib.check(lib.pyotf_b200_hanser_create(C.byref(p), stream_ptr(), C.byref(h)))
         self._h, self.precision, self.size = h, precision, int(size)
-        K, f0, nvec = C.c_int(), C.c_int(), C.c_int()
-        _lib.check(lib.pyotf_b200_hanser_info(h, C.byref(K), C.byref(f0), C.byref(nvec)))
-        self.K, self.f0, self.nvec = K.value, f0.value, nvec.value
+        K, KR, f0, nvec = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(lib.pyotf_b200_hanser_info(h, C.byref(K), C.byref(KR), C.byref(f0), C.byref(nvec)))
+        self.K, self.KR, self.f0, self.nvec = K.value, KR.value, f0.value, nvec.value
 
     def __del__(self):
         try:
@@ -79,18 +79,18 @@ class HanserHandle:
         """(kz [K,K] f64, amp [nvec,K,K], mask [K,K] u8) device tensors -- for tests."""
         torch = _torch()
         rt, _ = torch_dtypes(self.precision)
-        kz = torch.empty((self.K, self.K), dtype=torch.float64, device="cuda")
-        amp = torch.empty((self.nvec, self.K, self.K), dtype=rt, device="cuda")
-        mask = torch.empty((self.K, self.K), dtype=torch.uint8, device="cuda")
+        kz = torch.empty((self.KR, self.K), dtype=torch.float64, device="cuda")
+        amp = torch.empty((self.nvec, self.KR, self.K), dtype=rt, device="cuda")
+        mask = torch.empty((self.KR, self.K), dtype=torch.uint8, device="cuda")
         _lib.check(_lib.load().pyotf_b200_hanser_tables(self._h, ptr(kz), ptr(amp), ptr(mask), stream_ptr()))
-        return kz, amp, mask
+        return kz[:self.K], amp[:, :self.K], mask[:self.K]
 
     def pack_pupil(self, pupil_dev):
-        """[B,N,N] complex128 unshifted device tensor -> compact [B,K,K] in the handle's dtype."""
+        """[B,N,N] complex128 unshifted device tensor -> compact [B,KR,K] (zero-padded rows) in the handle's dtype."""
         torch = _torch()
         _, ct = torch_dtypes(self.precision)
         B = pupil_dev.shape[0]
-        out = torch.empty((B, self.K, self.K), dtype=ct, device="cuda")
+        out = torch.empty((B, self.KR, self.K), dtype=ct, device="cuda")
         _lib.check(_lib.load().pyotf_b200_hanser_pack_pupil(self._h, ptr(pupil_dev), B, ptr(out), stream_ptr()))
         return out
 
@@ -103,7 +103,7 @@ class HanserHandle:
         if pupilc is not None:
             if pupilc.dim() == 2:
                 pupilc = pupilc[None]
-            stride = self.K * self.K if pupilc.shape[0] > 1 else 0
+            stride = self.KR * self.K if pupilc.shape[0] > 1 else 0
             if pupilc.shape[0] > 1:
                 batch = pupilc.shape[0]
         if want_psfa and psfa_out is None:
@@ -194,7 +194,19 @@ def aberration_pupil(handle, n, m, mcoefs, pcoefs):
     mc = to_device_f64(np.atleast_2d(mcoefs)) if mcoefs is not None else None
     pc = to_device_f64(np.atleast_2d(pcoefs)) if pcoefs is not None else None
     nd, md = to_device_i32(n), to_device_i32(m)
-    out = torch.empty((B, handle.K, handle.K), dtype=ct, device="cuda")
+    out = torch.empty((B, handle.KR, handle.K), dtype=ct, device="cuda")
     _lib.check(_lib.load().pyotf_b200_hanser_aberration_pupil(handle._h, ptr(nd), ptr(md), nmodes, ptr(mc), ptr(pc), B,
                                                               ptr(out), stream_ptr()))
     return out
+
+
+def to_host(t):
+    """CUDA tensor -> numpy array through a pinned staging buffer (the array owns the buffer)."""
+    torch = _torch()
+    t = t.detach()
+    if not t.is_cuda:
+        return t.numpy()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()

@@ -45,7 +45,7 @@ def _digest():
 
 
 def build(force=False, verbose=False):
-    stamp = os.path.join(OBJ, "digest")
+    stamp = LIB + ".digest"
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB

@@ -15,13 +15,13 @@ static int aberration_launch(const pyotf_hanser* h, const int* n, const int* m, 
                              const double* pc, int batch, void* out, cudaStream_t s) {
     constexpr int PIX = 64;
     AberrationParams p;
-    p.N = h->N; p.K = h->K; p.f0 = h->f0; p.nmodes = nmodes; p.batch = batch;
+    p.N = h->N; p.K = h->K; p.KR = h->KR; p.f0 = h->f0; p.nmodes = nmodes; p.batch = batch;
     p.has_mag = mc != nullptr; p.has_phase = pc != nullptr;
     p.kstep = 1.0 / ((double)h->N * h->p.res); p.wl = h->p.wl; p.na = h->p.na; p.diff_limit = h->p.na / h->p.wl;
     size_t smem = sizeof(double) * ((size_t)nmodes * PIX + PIX);
     auto kern = aberration_pupil_kernel<T, PIX>;
     PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int KK = h->K * h->K;
+    int KK = h->KR * h->K;
     int gy = batch >= 256 ? 4 : 1;
     dim3 grid((unsigned)((KK + PIX - 1) / PIX), (unsigned)gy);
     kern<<<grid, 256, smem, s>>>(p, n, m, mc, pc, (cplx<T>*)out);
@@ -69,7 +69,8 @@ int pyotf_b200_hanser_create(const pyotf_hanser_params* p, void* stream, pyotf_h
     // row pitch == 8 (mod 16) elements keeps the two row groups of a half-warp on disjoint banks
     h->KP = h->K + ((8 - h->K % 16) + 16) % 16;
     h->nvec = p->vec_corr == PYOTF_VEC_NONE ? 1 : (p->vec_corr == PYOTF_VEC_TOTAL ? 6 : 2);
-    size_t KK = (size_t)h->K * h->K, es = p->dtype == PYOTF_F32 ? 4 : 8;
+    h->KR = h->K + PYOTF_PAD_ROWS;
+    size_t KK = (size_t)h->KR * h->K, es = p->dtype == PYOTF_F32 ? 4 : 8;
     cudaStream_t s = (cudaStream_t)stream;
     PYOTF_CUDA_OK(cudaMalloc(&h->kzc, KK * sizeof(double)));
     PYOTF_CUDA_OK(cudaMalloc(&h->ampc, KK * h->nvec * es));
@@ -88,9 +89,10 @@ int pyotf_b200_hanser_destroy(pyotf_hanser_t* h) {
     return 0;
 }
 
-int pyotf_b200_hanser_info(const pyotf_hanser_t* h, int* K, int* f0, int* nvec) {
+int pyotf_b200_hanser_info(const pyotf_hanser_t* h, int* K, int* rows, int* f0, int* nvec) {
     PYOTF_REQUIRE(h, "hanser_info: null handle");
     if (K) *K = h->K;
+    if (rows) *rows = h->KR;
     if (f0) *f0 = h->f0;
     if (nvec) *nvec = h->nvec;
     return 0;
@@ -100,7 +102,7 @@ int pyotf_b200_hanser_tables(const pyotf_hanser_t* h, double* kz_dev, void* amp_
                              void* stream) {
     PYOTF_REQUIRE(h, "hanser_tables: null handle");
     cudaStream_t s = (cudaStream_t)stream;
-    size_t KK = (size_t)h->K * h->K, es = h->p.dtype == PYOTF_F32 ? 4 : 8;
+    size_t KK = (size_t)h->KR * h->K, es = h->p.dtype == PYOTF_F32 ? 4 : 8;
     if (kz_dev) PYOTF_CUDA_OK(cudaMemcpyAsync(kz_dev, h->kzc, KK * 8, cudaMemcpyDeviceToDevice, s));
     if (amp_dev) PYOTF_CUDA_OK(cudaMemcpyAsync(amp_dev, h->ampc, KK * h->nvec * es, cudaMemcpyDeviceToDevice, s));
     if (mask_dev) PYOTF_CUDA_OK(cudaMemcpyAsync(mask_dev, h->maskc, KK, cudaMemcpyDeviceToDevice, s));

@@ -27,13 +27,14 @@ void set_error(const std::string& msg);
         }                                                                                        \
     } while (0)
 
+constexpr int PYOTF_PAD_ROWS = 64;   // >= the largest rows-per-CTA M of K1
 inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
 }  // namespace pyotf
 
 struct pyotf_hanser {
     pyotf_hanser_params p;
-    int N, K, KP, f0, nvec, device;
+    int N, K, KR, KP, f0, nvec, device;   // KR = K + PYOTF_PAD_ROWS rows allocated (zero padded)
     double* kzc = nullptr;          // [K*K]
     void* ampc = nullptr;           // [nvec*K*K] dtype
     unsigned char* maskc = nullptr; // [K*K]

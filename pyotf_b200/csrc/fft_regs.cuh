@@ -11,7 +11,8 @@
 
 namespace pyotf {
 
-template <typename T> struct cplx { T x, y; };
+// interleaved complex, aligned so that global / shared accesses are single 8 B / 16 B transactions
+template <typename T> struct alignas(2 * sizeof(T)) cplx { T x, y; };
 
 template <typename T> struct vec2;
 template <> struct vec2<float> { using type = float2; };

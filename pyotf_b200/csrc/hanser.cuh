@@ -31,6 +31,7 @@ template <> struct FftPlan<256> { static constexpr int R1 = 16, R2 = 16, G = 16;
 struct HanserGeomParams {
     int N;            // grid size
     int K;            // support box edge
+    int KR;           // allocated rows of the compact tables (K + zero padding rows)
     int f0;           // first frequency index of the box (negative)
     int nvec;         // 1, 2 or 6
     int vec_mode;     // 0 none, 1 x, 2 y, 3 z, 4 total
@@ -46,9 +47,15 @@ template <typename T>
 __global__ void hanser_geometry_kernel(HanserGeomParams p, double* __restrict__ kzc, T* __restrict__ ampc,
                                        unsigned char* __restrict__ maskc) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int KK = p.K * p.K;
+    int KK = p.KR * p.K;
     if (idx >= KK) return;
     int iy = idx / p.K, ix = idx - iy * p.K;
+    if (iy >= p.K) {                                            // zero padding rows
+        kzc[idx] = 0.0;
+        if (maskc) maskc[idx] = 0;
+        for (int v = 0; v < p.nvec; ++v) ampc[(size_t)v * KK + idx] = (T)0;
+        return;
+    }
     double ky = __dmul_rn((double)(p.f0 + iy), p.kstep);
     double kx = __dmul_rn((double)(p.f0 + ix), p.kstep);
     double kr = hypot(ky, kx);                                  // cart2pol(kyy, kxx)  utils.py:25-29
@@ -92,15 +99,16 @@ __global__ void twiddle_kernel(int N, cplx<T>* __restrict__ tw) {
     tw[k] = mk<T>((T)c, (T)s);
 }
 
-// user pupil (N x N complex128, unshifted like fftfreq) -> compact centred K x K in T
+// user pupil (N x N complex128, unshifted like fftfreq) -> compact centred [KR][K] in T
 template <typename T>
-__global__ void pack_pupil_kernel(int N, int K, int f0, const double2* __restrict__ src, cplx<T>* __restrict__ dst,
-                                  int batch) {
+__global__ void pack_pupil_kernel(int N, int K, int KR, int f0, const double2* __restrict__ src,
+                                  cplx<T>* __restrict__ dst, int batch) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int KK = K * K;
+    int KK = KR * K;
     if (idx >= KK * batch) return;
     int b = idx / KK, r = idx - b * KK;
     int iy = r / K, ix = r - iy * K;
+    if (iy >= K) { dst[idx] = mk<T>(0, 0); return; }
     int y = (f0 + iy) & (N - 1), x = (f0 + ix) & (N - 1);
     double2 v = src[(size_t)b * N * N + (size_t)y * N + x];
     dst[idx] = mk<T>((T)v.x, (T)v.y);
@@ -123,14 +131,14 @@ static __global__ void pupil_support_kernel(int N, const double2* __restrict__ s
 }
 
 template <typename T> struct HanserArgs {
-    const double* kzc;        // [K*K]   kz in cycles per length unit
-    const T* ampc;            // [nvec][K*K]
-    const cplx<T>* pupilc;    // [B][K*K] or nullptr
+    const double* kzc;        // [KR][K]   kz in cycles per length unit (rows >= K are zero)
+    const T* ampc;            // [nvec][KR][K]
+    const cplx<T>* pupilc;    // [B][KR][K] or nullptr
     const cplx<T>* tw;        // [N] e^{+2 pi i k/N}
     const double* z;          // [nz]
     T* psfi;                  // [B][nz][N][N] or nullptr
     cplx<T>* psfa;            // [B][nvec][nz][N][N] or nullptr
-    int K, KP, f0, nz, nvec;
+    int K, KR, KP, f0, nz, nvec;
     long long pupil_stride;   // elements between pupils in pupilc (0 = shared)
 };
 
@@ -140,12 +148,92 @@ template <int N, int M, typename T> struct HanserSmem {
     static constexpr int NG = NT / RP::G;                     // row groups per CTA
     static constexpr int PITCH = RP::R2 + 1;                  // exchange pitch (elements)
     static constexpr int EXSZ = ((RP::R1 * PITCH + 7) / 8) * 8 + (RP::G == 8 ? 8 : 0);
-    __host__ __device__ static size_t bytes(int KP) {
-        return sizeof(cplx<T>) * ((size_t)N + (size_t)M * KP + (size_t)NG * EXSZ);
+    // the defocus table (fold phase) and the row-exchange buffers (row phase) share one region
+    __host__ __device__ static size_t bytes(int KP, int ntab) {
+        size_t ex = (size_t)NG * EXSZ;
+        return sizeof(cplx<T>) * ((size_t)N + (size_t)M * KP + (ex > (size_t)ntab ? ex : (size_t)ntab));
     }
 };
 
-template <typename T, int N, int M>
+// Fold fused with the first column-FFT stage, for one thread's column kx and sub-row bp.
+// The pupil rows that reach this thread's Q1 bins (b = L1*q + bp) are exactly the rows with
+// f0 + iy == bp (mod L1), an arithmetic progression iy = iy0 + L1*j.  Row j lands in bin
+// q = (m0 + j) mod Q1, so it is accumulated into the compile-time slot xs[j mod Q1] and the
+// cyclic offset m0 is repaid after the butterfly as the phase w_Q1^{m0 c} (shift theorem),
+// merged into the stage twiddle.  Each group of Q1 rows is branch-free (clamped address,
+// zero weight when out of range) so its global loads issue back to back.
+template <bool TAB, bool HASP, typename T, int N, int M>
+__device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const cplx<T>* __restrict__ tws,
+                                                 const cplx<T>* __restrict__ Dq, const T* __restrict__ amp,
+                                                 const cplx<T>* __restrict__ pupil, const double* __restrict__ kzc,
+                                                 double z, int K, int KP, int f0, int r, int kx, int rl, int nrl) {
+    using CP = FftPlan<M>;
+    constexpr int R = N / M, Q1 = CP::R1, L1 = CP::R2, JMAX = N / L1;
+    const int fx = f0 + kx, ax = fx < 0 ? -fx : fx;
+    const int HP = 1 - f0;                                       // table pitch H + 1
+    const unsigned rowstride = (unsigned)K;
+    const T* __restrict__ ap = amp + kx;
+    const cplx<T>* __restrict__ pp = pupil + kx;
+    const double* __restrict__ kzp = kzc + kx;
+    // rot[t] = w_R^{t r}: phase between consecutive groups of Q1 rows (they are M rows apart)
+    cplx<T> rot[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) rot[t] = tws[(t * r * M) & (N - 1)];
+    for (int bp = rl; bp < L1; bp += nrl) {
+        const int iy0 = (bp - f0) & (L1 - 1);
+        const int m0 = (f0 + iy0 - bp) / L1;                      // exact
+        cplx<T> xs[Q1];
+#pragma unroll
+        for (int q = 0; q < Q1; ++q) xs[q] = mk<T>(0, 0);
+#pragma unroll
+        for (int jb = 0; jb < JMAX; jb += Q1) {
+            if (iy0 + L1 * jb >= K) break;                        // warp-uniform
+#pragma unroll
+            for (int u = 0; u < Q1; ++u) {
+                // rows >= K read the zero padding of the tables (KR = K + M rows), no clamp needed
+                const int iy = iy0 + L1 * (jb + u);
+                const int fy = f0 + iy;
+                const unsigned off = (unsigned)iy * rowstride;
+                cplx<T> d;
+                if constexpr (TAB) {
+                    int ay = fy < 0 ? -fy : fy;
+                    ay = ay < HP ? ay : HP - 1;                   // keep the lookup inside the table
+                    d = Dq[ay * HP + ax];
+                } else {
+                    cis_cycles(kzp[off] * z, d);                   // _calc_defocus   otf.py:357-360
+                }
+                const T am = ap[off];
+                cplx<T> p;
+                if constexpr (HASP) p = cmul(cscale(pp[off], am), d);
+                else p = cscale(d, am);
+                // w_N^{fy r} = w_N^{(bp + L1 (m0 + u)) r} * w_R^{(jb / Q1) r}: the second factor is
+                // CTA-uniform per group, the first is applied once per slot after the loop
+                if (jb == 0 || R == 1) xs[u] = xs[u] + p;
+                else {
+                    const cplx<T> w = rot[jb / Q1];
+                    xs[u].x += p.x * w.x - p.y * w.y;
+                    xs[u].y += p.x * w.y + p.y * w.x;
+                }
+            }
+        }
+        if constexpr (R > 1) {
+#pragma unroll
+            for (int u = 0; u < Q1; ++u) xs[u] = cmul(xs[u], tws[((bp + L1 * (m0 + u)) * r) & (N - 1)]);
+        }
+        fft_radix<1, Q1>(xs);
+#pragma unroll
+        for (int c = 0; c < Q1; ++c) {
+            if (c > 0) xs[c] = cmul(xs[c], tws[(bp * c * R + m0 * c * (N / Q1)) & (N - 1)]);
+            U[(c * L1 + bp) * KP + kx] = xs[c];
+        }
+    }
+}
+
+// TAB: the defocus factor exp(2 pi i kz z) depends on (|fy|, |fx|) only through fy^2 + fx^2, so
+// when the support box is symmetric each CTA evaluates it once per octant entry (i >= j >= 0)
+// into a shared-memory quadrant table instead of once per pupil pixel (6x fewer sincos for the
+// 256^2 configs).
+template <typename T, int N, int M, bool TAB>
 __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
     using RP = FftPlan<N>;
     using CP = FftPlan<M>;
@@ -156,75 +244,86 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
     cplx<T>* tws = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* U = tws + N;
     cplx<T>* EX = U + (size_t)M * a.KP;
+    cplx<T>* Dq = EX;                                            // aliases EX (disjoint phases)
 
     const int tid = threadIdx.x;
     const int r = blockIdx.x % R;
     const int plane = blockIdx.x / R;
     const int bidx = blockIdx.y;
-    const int K = a.K, KP = a.KP, f0 = a.f0, KK = K * K;
+    const int K = a.K, KP = a.KP, f0 = a.f0, KK = a.KR * K;
     const double z = a.z[plane];
-    const cplx<T>* pupil = a.pupilc ? a.pupilc + (size_t)bidx * a.pupil_stride : nullptr;
+    const cplx<T>* __restrict__ pupil = a.pupilc ? a.pupilc + (size_t)bidx * a.pupil_stride : nullptr;
+    const double* __restrict__ kzc = a.kzc;
 
     for (int i = tid; i < N; i += NT) tws[i] = a.tw[i];
 
-    // per-thread row-pass twiddles w_N^{b' c}, b' = lane in group
+    // per-thread row-pass twiddles w_N^{b' c} / N^2 (the ifft normalisation rides on them)
     const int g = tid % RP::G;
     const int grp = tid / RP::G;
+    const T scale = (T)1.0 / ((T)N * (T)N);
     cplx<T> twr[RP::R1];
 #pragma unroll
-    for (int c = 0; c < RP::R1; ++c) twr[c] = a.tw[(g * c) & (N - 1)];
+    for (int c = 0; c < RP::R1; ++c) twr[c] = cscale(a.tw[(g * c) & (N - 1)], scale);
 
-    const T scale = (T)1.0 / ((T)N * (T)N);
+    // column-parallel mapping for fold + column FFT: a warp owns 32 consecutive kx
+    const int ncw = (K + 31) >> 5;                 // warps needed to cover the K columns
+    const int nrl = (NT / 32) / ncw;               // row lanes (>= 1 because K <= 256)
+    const int kx = ((tid >> 5) % ncw) * 32 + (tid & 31);
+    const int rl = (tid >> 5) / ncw;
+    const bool colactive = rl < nrl && kx < K;
+
     const size_t plane_elems = (size_t)N * N;
 
     for (int v = 0; v < a.nvec; ++v) {
-        __syncthreads();
-        // ---------------- fold ----------------
-        const T* amp = a.ampc + (size_t)v * KK;
-        for (int w = tid; w < M * K; w += NT) {
-            int b = w / K, kx = w - b * K;
-            int off = (b - f0) % M; if (off < 0) off += M;
-            cplx<T> acc = mk<T>(0, 0);
-            for (int iy = off; iy < K; iy += M) {
-                int idx = iy * K + kx;
-                T am = amp[idx];
-                cplx<T> p = pupil ? cscale(pupil[idx], am) : mk<T>(am, 0);
-                if (p.x != (T)0 || p.y != (T)0) {
-                    cplx<T> d;
-                    cis_cycles(a.kzc[idx] * z, d);             // _calc_defocus   otf.py:357-360
-                    p = cmul(p, d);
-                    if (R > 1) p = cmul(p, tws[((f0 + iy) * r) & (N - 1)]);
-                    acc = acc + p;
+        __syncthreads();                                         // previous component's rows are done with EX
+        if constexpr (TAB) {
+            const int H = -f0, HP = H + 1, ntri = (H + 1) * (H + 2) / 2;
+            for (int e0 = tid; e0 < ntri; e0 += 4 * NT) {
+                double kzv[4];
+                int ii[4], jj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {                  // issue the four loads before any sincos
+                    const int e = e0 + u * NT;
+                    ii[u] = -1; jj[u] = 0; kzv[u] = 0.0;
+                    if (e < ntri) {
+                        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+                        if (i * (i + 1) / 2 > e) --i;
+                        if ((i + 1) * (i + 2) / 2 <= e) ++i;
+                        ii[u] = i; jj[u] = e - i * (i + 1) / 2;
+                        kzv[u] = kzc[(H + i) * K + (H + jj[u])];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ii[u] >= 0) {
+                        cplx<T> d;
+                        cis_cycles(kzv[u] * z, d);             // _calc_defocus   otf.py:357-360
+                        Dq[ii[u] * HP + jj[u]] = d;
+                        Dq[jj[u] * HP + ii[u]] = d;
+                    }
                 }
             }
-            U[b * KP + kx] = acc;
         }
         __syncthreads();
-        // ---------------- columns: FFT_M over b, in place, digit-reversed rows ----------------
+        // ---------------- fold + first column stage (registers), in place ----------------
+        const T* __restrict__ amp = a.ampc + (size_t)v * KK;
         {
             constexpr int Q1 = CP::R1, L1 = CP::R2;
-            for (int w = tid; w < L1 * K; w += NT) {
-                int bp = w / K, kx = w - bp * K;
-                cplx<T> x[Q1];
-#pragma unroll
-                for (int q = 0; q < Q1; ++q) x[q] = U[(L1 * q + bp) * KP + kx];
-                fft_radix<1, Q1>(x);
-#pragma unroll
-                for (int c = 0; c < Q1; ++c) {
-                    if (L1 > 1 && c > 0) x[c] = cmul(x[c], tws[(bp * c * R) & (N - 1)]);
-                    U[(c * L1 + bp) * KP + kx] = x[c];
-                }
+            if (colactive) {
+                if (pupil) hanser_fold_cols<TAB, true, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
+                else hanser_fold_cols<TAB, false, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
             }
             if constexpr (L1 > 1) {
                 __syncthreads();
-                for (int w = tid; w < Q1 * K; w += NT) {
-                    int c1 = w / K, kx = w - c1 * K;
-                    cplx<T> x[L1];
+                if (colactive) {
+                    for (int c1 = rl; c1 < Q1; c1 += nrl) {
+                        cplx<T> x[L1];
 #pragma unroll
-                    for (int q = 0; q < L1; ++q) x[q] = U[(c1 * L1 + q) * KP + kx];
-                    fft_radix<1, L1>(x);
+                        for (int q = 0; q < L1; ++q) x[q] = U[(c1 * L1 + q) * KP + kx];
+                        fft_radix<1, L1>(x);
 #pragma unroll
-                    for (int q = 0; q < L1; ++q) U[(c1 * L1 + q) * KP + kx] = x[q];
+                        for (int q = 0; q < L1; ++q) U[(c1 * L1 + q) * KP + kx] = x[q];
+                    }
                 }
             }
         }
@@ -234,26 +333,26 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
             constexpr int R1 = RP::R1, L1 = RP::R2, G = RP::G, NG = SM::NG, PITCH = SM::PITCH;
             constexpr int CL1 = CP::R2, CQ1 = CP::R1;
             cplx<T>* ex = EX + (size_t)grp * SM::EXSZ;
+            const int ipos = g - f0;                 // U index of frequency k = g (positive half)
+            const int ineg = g - f0 - N;             // U index of k = g when k - N is meant (negative half)
+            T* const psfi_plane = a.psfi ? a.psfi + ((size_t)bidx * a.nz + plane) * plane_elems : nullptr;
+            cplx<T>* const psfa_plane =
+                a.psfa ? a.psfa + (((size_t)bidx * a.nvec + v) * a.nz + plane) * plane_elems : nullptr;
             for (int l = grp; l < M; l += NG) {
                 const int yp = (l / CL1) + CQ1 * (l % CL1);
-                const int y = R * yp + r;
-                const int ys = (y + N / 2) & (N - 1);
+                const int ys = (R * yp + r + N / 2) & (N - 1);
                 const cplx<T>* Ul = U + (size_t)l * KP;
                 cplx<T> x[R1];
 #pragma unroll
                 for (int q = 0; q < R1; ++q) {
-                    int k = L1 * q + g;
-                    int f = k < N / 2 ? k : k - N;
-                    int i = f - f0;
-                    x[q] = (i >= 0 && i < K) ? Ul[i] : mk<T>(0, 0);
+                    // k = L1*q + g ; positive half k < N/2, else frequency k - N
+                    if (L1 * q < N / 2) x[q] = (ipos + L1 * q < K) ? Ul[ipos + L1 * q] : mk<T>(0, 0);
+                    else x[q] = (ineg + L1 * q >= 0) ? Ul[ineg + L1 * q] : mk<T>(0, 0);
                 }
                 fft_radix<1, R1>(x);
                 __syncwarp();
 #pragma unroll
-                for (int c = 0; c < R1; ++c) {
-                    if (c > 0) x[c] = cmul(x[c], twr[c]);
-                    ex[c * PITCH + g] = x[c];
-                }
+                for (int c = 0; c < R1; ++c) ex[c * PITCH + g] = cmul(x[c], twr[c]);
                 __syncwarp();
 #pragma unroll
                 for (int u = 0; u < R1 / G; ++u) {
@@ -262,20 +361,25 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
 #pragma unroll
                     for (int q = 0; q < L1; ++q) t[q] = ex[c1 * PITCH + q];
                     fft_radix<1, L1>(t);
+                    // output x = c1 + R1*c2, stored fftshift-ed: (x + N/2) mod N
+                    if (psfa_plane) {
+                        cplx<T>* row = psfa_plane + (size_t)ys * N + c1;
 #pragma unroll
-                    for (int c2 = 0; c2 < L1; ++c2) {
-                        const int xo = c1 + R1 * c2;
-                        const int xs = (xo + N / 2) & (N - 1);
-                        cplx<T> o = cscale(t[c2], scale);
-                        if (a.psfa) {
-                            size_t pa = (((size_t)bidx * a.nvec + v) * a.nz + plane) * plane_elems + (size_t)ys * N + xs;
-                            a.psfa[pa] = o;
-                        }
-                        if (a.psfi) {
-                            size_t pi = ((size_t)bidx * a.nz + plane) * plane_elems + (size_t)ys * N + xs;
-                            T in = o.x * o.x + o.y * o.y;
-                            if (v > 0) in += a.psfi[pi];
-                            a.psfi[pi] = in;
+                        for (int c2 = 0; c2 < L1; ++c2)
+                            row[R1 * c2 < N / 2 ? R1 * c2 + N / 2 : R1 * c2 - N / 2] = t[c2];
+                    }
+                    if (psfi_plane) {
+                        T* row = psfi_plane + (size_t)ys * N + c1;
+                        if (v == 0) {
+#pragma unroll
+                            for (int c2 = 0; c2 < L1; ++c2)
+                                row[R1 * c2 < N / 2 ? R1 * c2 + N / 2 : R1 * c2 - N / 2] =
+                                    t[c2].x * t[c2].x + t[c2].y * t[c2].y;
+                        } else {
+#pragma unroll
+                            for (int c2 = 0; c2 < L1; ++c2)
+                                row[R1 * c2 < N / 2 ? R1 * c2 + N / 2 : R1 * c2 - N / 2] +=
+                                    t[c2].x * t[c2].x + t[c2].y * t[c2].y;
                         }
                     }
                 }

@@ -57,7 +57,7 @@ static __global__ void zernike_eval_kernel(const double* __restrict__ r, const d
 }
 
 struct AberrationParams {
-    int N, K, f0;
+    int N, K, KR, f0;
     int nmodes, batch;
     int has_mag, has_phase;
     double kstep, wl, na, diff_limit;
@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256) aberration_pupil_kernel(AberrationParams 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Z = reinterpret_cast<double*>(smem_raw);            // [nmodes][PIX]
     double* ideal = Z + (size_t)p.nmodes * PIX;                 // [PIX]
-    const int KK = p.K * p.K;
+    const int KK = p.K * p.K;                 // real pixels; the padded layout has KR * K
+    const int KKP = p.KR * p.K;
     const int pix0 = blockIdx.x * PIX;
     for (int w = threadIdx.x; w < PIX * p.nmodes; w += blockDim.x) {
         int j = w / PIX, q = w - j * PIX;
@@ -98,7 +99,12 @@ __global__ void __launch_bounds__(256) aberration_pupil_kernel(AberrationParams 
     const int bl = threadIdx.x / PIX;
     const int nbl = blockDim.x / PIX;
     const int idx = pix0 + q;
-    if (idx >= KK) return;
+    if (idx >= KKP) return;
+    if (idx >= KK) {                                             // zero padding rows
+        for (int b = blockIdx.y * nbl + bl; b < p.batch; b += nbl * gridDim.y)
+            pupilc[(size_t)b * KKP + idx] = mk<T>(0, 0);
+        return;
+    }
     for (int b = blockIdx.y * nbl + bl; b < p.batch; b += nbl * gridDim.y) {
         double mag = 0.0, ph = 0.0;
         if (p.has_mag) {
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(256) aberration_pupil_kernel(AberrationParams 
         mag += ideal[q];                                         // otf.py:639
         double s, c;
         sincos(ph, &s, &c);
-        pupilc[(size_t)b * KK + idx] = mk<T>((T)(mag * c), (T)(mag * s));
+        pupilc[(size_t)b * KKP + idx] = mk<T>((T)(mag * c), (T)(mag * s));
     }
 }
 

@@ -32,7 +32,7 @@ def _result_property(name, doc):
     def getter(self):
         host = self.__dict__.setdefault("_results", {})
         if name not in host:
-            host[name] = self._device_result(name).detach().cpu().numpy()
+            host[name] = _engine.to_host(self._device_result(name))
         return host[name]
 
     def setter(self, value):
