@@ -107,6 +107,55 @@ int pyotf_b200_hanser_aberration_pupil(const pyotf_hanser_t* h, const int* n_dev
                                        void* pupilc_out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Phase retrieval  (pyotf/phaseretrieval.py:32-149, the loop :95-135, _calc_mse :401-403)
+ * ---------------------------------------------------------------------------------- */
+typedef struct pyotf_pr pyotf_pr_t;
+typedef struct pyotf_comm pyotf_comm_t;
+
+/* K2 state for one measured stack.  `params` as for HanserPSF; vec_corr / condition / support
+ * are overridden (retrieve_phase forces "none"/"none", phaseretrieval.py:74-76).
+ *   z_dev        [nz] float64 plane positions of THIS rank's planes
+ *   nz_total     planes over all ranks (== nz on one GPU): the z-mean and the MSE divide by it
+ *   data_dev     [nz][N][N] measured intensities, fftshift-ed like PSFi; data_dtype PYOTF_F32/F64
+ *   rows_per_cta 0 = auto, else 16 | 32 | 64 (tuning knob: output rows of a plane per CTA)
+ * The pupil estimate starts as the ideal pupil (HanserPSF._gen_pupil, phaseretrieval.py:89). */
+int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev, int nz, long long nz_total,
+                         const void* data_dev, int data_dtype, int rows_per_cta, void* stream, pyotf_pr_t** out);
+int pyotf_b200_pr_destroy(pyotf_pr_t* s);
+/* K, rows, f0 of the compact pupil layout; rows per CTA; partial pupils per iteration */
+int pyotf_b200_pr_info(const pyotf_pr_t* s, int* K, int* rows, int* f0, int* rows_per_cta, int* nparts);
+/* Replace the current pupil estimate by an unshifted N x N complex128 pupil (NULL: the ideal
+ * pupil again).  Lets a caller re-seed single iterations (parity tests) or warm-start. */
+int pyotf_b200_pr_set_pupil(pyotf_pr_t* s, const void* pupil_c128_dev, void* stream);
+/* which = 0: the final new_pupil (phaseretrieval.py:144-148); 1: the pupil last applied to the
+ * model (what result.model.PSFi shows).  Output: unshifted N x N complex128. */
+int pyotf_b200_pr_get_pupil(const pyotf_pr_t* s, int which, void* pupil_c128_dev_out, void* stream);
+/* Runs up to max_iters iterations of the loop, the convergence test
+ * (pupil_diff < pupil_tol || mse_diff < mse_tol || mse < mse_tol, :114) evaluated on the device.
+ * comm != NULL: planes are sharded over the ranks of `comm`; one all-reduce per iteration.
+ * Host outputs (any may be NULL) hold iters_run entries each, like the reference's trimmed
+ * arrays (:133-135).  SYNCHRONISES the stream before returning. */
+int pyotf_b200_pr_run(pyotf_pr_t* s, int max_iters, double pupil_tol, double mse_tol, int phase_only,
+                      pyotf_comm_t* comm, double* mse_host, double* mse_diff_host, double* pupil_diff_host,
+                      int* iters_run_host, void* stream);
+
+/* HOST function (host pointers): 2D phase unwrapping of one ny x nx image of wrapped phases,
+ * Herraez et al. 2002 -- stand-in for skimage.restoration.unwrap_phase (phaseretrieval.py:146). */
+int pyotf_b200_unwrap_phase_2d(const double* in_host, double* out_host, int ny, int nx);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU plumbing (one process per GPU)
+ * ---------------------------------------------------------------------------------- */
+/* dlopen the NCCL library the host process uses (path of libnccl.so.2; NULL/"" = default search) */
+int pyotf_b200_comm_load(const char* libnccl_path);
+/* rank 0 creates the 128-byte id and distributes it (torch.distributed / any side channel) */
+int pyotf_b200_comm_unique_id(unsigned char id_out[128]);
+int pyotf_b200_comm_create(const unsigned char id[128], int rank, int world, pyotf_comm_t** out);
+int pyotf_b200_comm_destroy(pyotf_comm_t* c);
+/* in-place sum all-reduce of n float64 on `stream` */
+int pyotf_b200_comm_allreduce_f64(pyotf_comm_t* c, double* buf_dev, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Shifted N-d FFT  (pyotf/utils.py:15-22; OTFi otf.py:209-212; OTFa otf.py:435-438, 589-592)
  * ---------------------------------------------------------------------------------- */
 /* out = [fftshift](fftn)([ifftshift] in) over `axes` (forward), or

@@ -115,6 +115,132 @@ class HanserHandle:
         return psfa_out, psfi_out
 
 
+class PRState:
+    """Owns one pyotf_pr_t: the device state of a phase retrieval on one measured stack (K2)."""
+
+    def __init__(self, wl, na, ni, res, size, zrange, data_dev, precision, nz_total=None, rows_per_cta=0):
+        lib = _lib.load()
+        torch = _torch()
+        if data_dev.dtype == torch.float32:
+            dcode = 0
+        elif data_dev.dtype == torch.float64:
+            dcode = 1
+        else:
+            raise TypeError(f"data must be float32 or float64 on the device, not {data_dev.dtype}")
+        data_dev = data_dev.contiguous()
+        nz = int(data_dev.shape[0])
+        z = to_device_f64(np.asarray(zrange, dtype=np.float64))
+        if z.numel() != nz:
+            raise ValueError(f"{nz} planes of data but {z.numel()} z positions")
+        p = _lib.HanserParams(float(wl), float(na), float(ni), float(res), int(size), 0, 0, dtype_code(precision), -2)
+        h = C.c_void_p()
+        _lib.check(lib.pyotf_b200_pr_create(C.byref(p), ptr(z), nz, int(nz if nz_total is None else nz_total),
+                                            ptr(data_dev), dcode, int(rows_per_cta), stream_ptr(), C.byref(h)))
+        self._h, self.precision, self.size, self.nz = h, precision, int(size), nz
+        K, KR, f0, M, nparts = (C.c_int() for _ in range(5))
+        _lib.check(lib.pyotf_b200_pr_info(h, C.byref(K), C.byref(KR), C.byref(f0), C.byref(M), C.byref(nparts)))
+        self.K, self.KR, self.f0, self.rows_per_cta, self.nparts = K.value, KR.value, f0.value, M.value, nparts.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().pyotf_b200_pr_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def set_pupil(self, pupil_dev=None):
+        """Re-seed the estimate from an unshifted [N, N] complex128 device tensor (None: ideal pupil)."""
+        if pupil_dev is not None:
+            pupil_dev = pupil_dev.contiguous()
+        _lib.check(_lib.load().pyotf_b200_pr_set_pupil(self._h, ptr(pupil_dev), stream_ptr()))
+
+    def get_pupil(self, applied=False):
+        """Unshifted [N, N] complex128 device tensor: the final pupil, or the last applied one."""
+        torch = _torch()
+        out = torch.empty((self.size, self.size), dtype=torch.complex128, device="cuda")
+        _lib.check(_lib.load().pyotf_b200_pr_get_pupil(self._h, int(bool(applied)), ptr(out), stream_ptr()))
+        return out
+
+    def run(self, max_iters, pupil_tol, mse_tol, phase_only=False, comm=None):
+        """Iterate on the device; returns (mse, mse_diff, pupil_diff) trimmed to the iterations run."""
+        mse, msed, pd = (np.empty(int(max_iters), dtype=np.float64) for _ in range(3))
+        n = C.c_int(0)
+        _lib.check(_lib.load().pyotf_b200_pr_run(
+            self._h, int(max_iters), float(pupil_tol), float(mse_tol), int(bool(phase_only)),
+            comm._h if comm is not None else C.c_void_p(0), mse.ctypes.data_as(C.c_void_p),
+            msed.ctypes.data_as(C.c_void_p), pd.ctypes.data_as(C.c_void_p), C.byref(n), stream_ptr()))
+        k = n.value
+        return mse[:k], msed[:k], pd[:k]
+
+
+class Comm:
+    """NCCL communicator owned by the C library (one process per GPU).
+
+    Rank 0 creates the unique id; it travels through ``torch.distributed`` (any backend)."""
+
+    def __init__(self, rank=None, world=None):
+        torch = _torch()
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        rank = dist.get_rank() if rank is None else rank
+        world = dist.get_world_size() if world is None else world
+        _lib.check(lib.pyotf_b200_comm_load(nccl_library_path().encode()))
+        idbuf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(lib.pyotf_b200_comm_unique_id(C.cast(idbuf, C.c_void_p)))
+        obj = [bytes(idbuf)]
+        dist.broadcast_object_list(obj, src=0)
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(obj[0])
+        h = C.c_void_p()
+        _lib.check(lib.pyotf_b200_comm_create(C.cast(idbuf, C.c_void_p), int(rank), int(world), C.byref(h)))
+        self._h, self.rank, self.world = h, rank, world
+        torch.cuda.synchronize()
+
+    def allreduce_f64(self, t):
+        _lib.check(_lib.load().pyotf_b200_comm_allreduce_f64(self._h, ptr(t), t.numel(), stream_ptr()))
+        return t
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().pyotf_b200_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_library_path():
+    """Path of the libnccl.so.2 this process (torch) already has mapped, else the default soname."""
+    try:
+        with open("/proc/self/maps") as f:
+            for line in f:
+                if "libnccl.so" in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
+    try:
+        import nvidia.nccl
+
+        cand = os.path.join(os.path.dirname(nvidia.nccl.__path__[0] + "/"), "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous block [lo, hi) of n items owned by `rank` (np.array_split sizes)."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
 _handles = {}
 _handles_lock = threading.Lock()
 

@@ -44,6 +44,18 @@ PROTOTYPES = {
     "pyotf_b200_fftn": (_i, [_vp, _vp, _i, C.POINTER(_ll), _ip, _i, _i, _i, _i, _i, _i, _vp]),
     "pyotf_b200_abs2_sum0": (_i, [_vp, _i, _ll, _vp, _i, _vp]),
     "pyotf_b200_hanser_aberration_pupil": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "pyotf_b200_pr_create": (_i, [C.POINTER(HanserParams), _vp, _i, _ll, _vp, _i, _i, _vp, C.POINTER(_vp)]),
+    "pyotf_b200_pr_destroy": (_i, [_vp]),
+    "pyotf_b200_pr_info": (_i, [_vp, _ip, _ip, _ip, _ip, _ip]),
+    "pyotf_b200_pr_set_pupil": (_i, [_vp, _vp, _vp]),
+    "pyotf_b200_pr_get_pupil": (_i, [_vp, _i, _vp, _vp]),
+    "pyotf_b200_pr_run": (_i, [_vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _ip, _vp]),
+    "pyotf_b200_unwrap_phase_2d": (_i, [_vp, _vp, _i, _i]),
+    "pyotf_b200_comm_load": (_i, [C.c_char_p]),
+    "pyotf_b200_comm_unique_id": (_i, [_vp]),
+    "pyotf_b200_comm_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "pyotf_b200_comm_destroy": (_i, [_vp]),
+    "pyotf_b200_comm_allreduce_f64": (_i, [_vp, _vp, _ll, _vp]),
 }
 
 

@@ -183,6 +183,75 @@ int pyotf_b200_hanser_aberration_pupil(const pyotf_hanser_t* h, const int* n, co
                                    : aberration_launch<double>(h, n, m, nmodes, mc, pc, batch, out, s);
 }
 
+int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev, int nz, long long nz_total,
+                         const void* data_dev, int data_dtype, int rows_per_cta, void* stream, pyotf_pr_t** out) {
+    PYOTF_REQUIRE(params && z_dev && data_dev && out, "pr_create: null argument");
+    PYOTF_REQUIRE(nz > 0 && nz_total >= nz, "pr_create: bad nz / nz_total");
+    PYOTF_REQUIRE(data_dtype == PYOTF_F32 || data_dtype == PYOTF_F64, "pr_create: bad data dtype");
+    PYOTF_REQUIRE(params->size <= 256, "pr_create: size must be one of 32, 64, 128, 256 on the fused path");
+    pyotf_hanser_params p = *params;
+    p.vec_corr = PYOTF_VEC_NONE; p.condition = PYOTF_COND_NONE; p.support = -2;   // phaseretrieval.py:74-76
+    pyotf_pr* s = new pyotf_pr();
+    int rc = pyotf_b200_hanser_create(&p, stream, &s->h);
+    if (rc) { delete s; return rc; }
+    s->nz = nz; s->nz_total = nz_total;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMalloc(&s->z, sizeof(double) * nz);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->z, z_dev, sizeof(double) * nz, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { set_error(std::string("pr_create: ") + cudaGetErrorString(e)); pyotf_b200_pr_destroy(s); return 2; }
+    rc = p.dtype == PYOTF_F32 ? pr_setup<float>(s, data_dev, data_dtype, rows_per_cta, st)
+                              : pr_setup<double>(s, data_dev, data_dtype, rows_per_cta, st);
+    if (rc) { pyotf_b200_pr_destroy(s); return rc; }
+    *out = s;
+    return 0;
+}
+
+int pyotf_b200_pr_destroy(pyotf_pr_t* s) {
+    if (!s) return 0;
+    cudaFree(s->z); cudaFree(s->data); cudaFree(s->pupil[0]); cudaFree(s->pupil[1]); cudaFree(s->partial);
+    cudaFree(s->mse_part); cudaFree(s->sums); cudaFree(s->diffpart); cudaFree(s->mse); cudaFree(s->mse_diff);
+    cudaFree(s->pupil_diff); cudaFree(s->state);
+    if (s->h_flags) { cudaFreeHost(s->h_flags); for (int i = 0; i < 4; ++i) cudaEventDestroy(s->ev[i]); }
+    pyotf_b200_hanser_destroy(s->h);
+    delete s;
+    return 0;
+}
+
+int pyotf_b200_pr_info(const pyotf_pr_t* s, int* K, int* rows, int* f0, int* rows_per_cta, int* nparts) {
+    PYOTF_REQUIRE(s, "pr_info: null handle");
+    if (K) *K = s->h->K;
+    if (rows) *rows = s->h->KR;
+    if (f0) *f0 = s->h->f0;
+    if (rows_per_cta) *rows_per_cta = s->M;
+    if (nparts) *nparts = s->nparts;
+    return 0;
+}
+
+int pyotf_b200_pr_set_pupil(pyotf_pr_t* s, const void* pupil_c128_dev, void* stream) {
+    PYOTF_REQUIRE(s, "pr_set_pupil: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    return s->h->p.dtype == PYOTF_F32 ? pr_set_pupil<float>(s, pupil_c128_dev, st) : pr_set_pupil<double>(s, pupil_c128_dev, st);
+}
+
+int pyotf_b200_pr_get_pupil(const pyotf_pr_t* s, int which, void* out, void* stream) {
+    PYOTF_REQUIRE(s && out && (which == 0 || which == 1), "pr_get_pupil: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    return s->h->p.dtype == PYOTF_F32 ? pr_get_pupil<float>(s, which, out, st) : pr_get_pupil<double>(s, which, out, st);
+}
+
+int pyotf_b200_pr_run(pyotf_pr_t* s, int max_iters, double pupil_tol, double mse_tol, int phase_only,
+                      pyotf_comm_t* comm, double* mse_host, double* mse_diff_host, double* pupil_diff_host,
+                      int* iters_run_host, void* stream) {
+    PYOTF_REQUIRE(s, "pr_run: null handle");
+    PYOTF_REQUIRE(max_iters > 0, "pr_run: Must have at least one iteration");
+    cudaStream_t st = (cudaStream_t)stream;
+    return s->h->p.dtype == PYOTF_F32
+               ? pr_run<float>(s, max_iters, pupil_tol, mse_tol, phase_only, comm, mse_host, mse_diff_host,
+                               pupil_diff_host, iters_run_host, st)
+               : pr_run<double>(s, max_iters, pupil_tol, mse_tol, phase_only, comm, mse_host, mse_diff_host,
+                                pupil_diff_host, iters_run_host, st);
+}
+
 int pyotf_b200_fftn(const void* in, void* out, int ndim, const long long* shape, const int* axes, int naxes, int inverse,
                     int real_in, int shift_in, int shift_out, int dtype, void* stream) {
     PYOTF_REQUIRE(in && out && shape && axes, "fftn: null argument");

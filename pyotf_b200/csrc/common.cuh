@@ -41,7 +41,36 @@ struct pyotf_hanser {
     void* tw = nullptr;             // [N] complex dtype
 };
 
+struct pyotf_comm;
+
+// phase-retrieval state (K2); buffers are in the handle's dtype unless noted
+struct pyotf_pr {
+    pyotf_hanser* h = nullptr;      // owned geometry (support = -2, vec_corr / condition = none)
+    int nz = 0, M = 0, nparts = 0, nblk = 0, cap_iters = 0;
+    long long nz_total = 0;         // planes over all ranks of a z-sharded retrieval
+    int cur = 0, applied = 0;       // pupil buffer holding the final / the last applied pupil
+    int launched = 0;               // iterations enqueued by the last run
+    double* z = nullptr;            // [nz]
+    void* data = nullptr;           // [nz][N][N]
+    void* pupil[2] = {nullptr, nullptr};   // [KR][K] complex
+    void* partial = nullptr;        // [nparts][K][K] complex
+    double* mse_part = nullptr;     // [nparts]
+    void* sums = nullptr;           // [K*K + 1] double2 (all-reduce buffer)
+    double* diffpart = nullptr;     // [2][nblk][2]
+    double *mse = nullptr, *mse_diff = nullptr, *pupil_diff = nullptr;   // [cap_iters]
+    void* state = nullptr;          // PrState
+    int* h_flags = nullptr;         // pinned: early-stop polling
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
 namespace pyotf {
+// K2 (pr_f32.cu / pr_f64.cu)
+template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype, int want_rows, cudaStream_t st);
+template <typename T> int pr_set_pupil(pyotf_pr* s, const void* pupil_c128, cudaStream_t st);
+template <typename T> int pr_get_pupil(const pyotf_pr* s, int which, void* out_c128, cudaStream_t st);
+template <typename T>
+int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int phase_only, pyotf_comm* comm,
+           double* mse_host, double* mse_diff_host, double* pupil_diff_host, int* iters_run_host, cudaStream_t st);
 // per-dtype launchers (hanser_f32.cu / hanser_f64.cu)
 template <typename T> int hanser_build_tables(pyotf_hanser* h, cudaStream_t s);
 template <typename T>

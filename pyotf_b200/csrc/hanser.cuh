@@ -155,6 +155,40 @@ template <int N, int M, typename T> struct HanserSmem {
     }
 };
 
+// Quadrant table of the defocus factor: Dq[|fy|][|fx|] = exp(2 pi i kz(|fy|,|fx|) z), pitch H + 1.
+// kz depends on fy^2 + fx^2 only, so each octant entry (i >= j >= 0) is evaluated once
+// (HanserPSF._calc_defocus, pyotf/otf.py:357-360).
+template <typename T, int NT>
+__device__ __forceinline__ void hanser_build_dtab(cplx<T>* __restrict__ Dq, const double* __restrict__ kzc, double z,
+                                                  int f0, int K, int tid) {
+    const int H = -f0, HP = H + 1, ntri = (H + 1) * (H + 2) / 2;
+    for (int e0 = tid; e0 < ntri; e0 += 4 * NT) {
+        double kzv[4];
+        int ii[4], jj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                  // issue the four loads before any sincos
+            const int e = e0 + u * NT;
+            ii[u] = -1; jj[u] = 0; kzv[u] = 0.0;
+            if (e < ntri) {
+                int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+                if (i * (i + 1) / 2 > e) --i;
+                if ((i + 1) * (i + 2) / 2 <= e) ++i;
+                ii[u] = i; jj[u] = e - i * (i + 1) / 2;
+                kzv[u] = kzc[(H + i) * K + (H + jj[u])];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ii[u] >= 0) {
+                cplx<T> d;
+                cis_cycles(kzv[u] * z, d);
+                Dq[ii[u] * HP + jj[u]] = d;
+                Dq[jj[u] * HP + ii[u]] = d;
+            }
+        }
+    }
+}
+
 // Fold fused with the first column-FFT stage, for one thread's column kx and sub-row bp.
 // The pupil rows that reach this thread's Q1 bins (b = L1*q + bp) are exactly the rows with
 // f0 + iy == bp (mod L1), an arithmetic progression iy = iy0 + L1*j.  Row j lands in bin
@@ -162,7 +196,7 @@ template <int N, int M, typename T> struct HanserSmem {
 // cyclic offset m0 is repaid after the butterfly as the phase w_Q1^{m0 c} (shift theorem),
 // merged into the stage twiddle.  Each group of Q1 rows is branch-free (clamped address,
 // zero weight when out of range) so its global loads issue back to back.
-template <bool TAB, bool HASP, typename T, int N, int M>
+template <bool TAB, bool HASP, typename T, int N, int M, bool AMP = true>
 __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const cplx<T>* __restrict__ tws,
                                                  const cplx<T>* __restrict__ Dq, const T* __restrict__ amp,
                                                  const cplx<T>* __restrict__ pupil, const double* __restrict__ kzc,
@@ -202,10 +236,15 @@ __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const 
                 } else {
                     cis_cycles(kzp[off] * z, d);                   // _calc_defocus   otf.py:357-360
                 }
-                const T am = ap[off];
                 cplx<T> p;
-                if constexpr (HASP) p = cmul(cscale(pp[off], am), d);
-                else p = cscale(d, am);
+                if constexpr (AMP) {
+                    const T am = ap[off];
+                    if constexpr (HASP) p = cmul(cscale(pp[off], am), d);
+                    else p = cscale(d, am);
+                } else {                                          // unit apodisation (phase retrieval)
+                    static_assert(HASP || AMP, "a pupil or an amplitude table is required");
+                    p = cmul(pp[off], d);
+                }
                 // w_N^{fy r} = w_N^{(bp + L1 (m0 + u)) r} * w_R^{(jb / Q1) r}: the second factor is
                 // CTA-uniform per group, the first is applied once per slot after the loop
                 if (jb == 0 || R == 1) xs[u] = xs[u] + p;
@@ -276,34 +315,7 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
 
     for (int v = 0; v < a.nvec; ++v) {
         __syncthreads();                                         // previous component's rows are done with EX
-        if constexpr (TAB) {
-            const int H = -f0, HP = H + 1, ntri = (H + 1) * (H + 2) / 2;
-            for (int e0 = tid; e0 < ntri; e0 += 4 * NT) {
-                double kzv[4];
-                int ii[4], jj[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {                  // issue the four loads before any sincos
-                    const int e = e0 + u * NT;
-                    ii[u] = -1; jj[u] = 0; kzv[u] = 0.0;
-                    if (e < ntri) {
-                        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-                        if (i * (i + 1) / 2 > e) --i;
-                        if ((i + 1) * (i + 2) / 2 <= e) ++i;
-                        ii[u] = i; jj[u] = e - i * (i + 1) / 2;
-                        kzv[u] = kzc[(H + i) * K + (H + jj[u])];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (ii[u] >= 0) {
-                        cplx<T> d;
-                        cis_cycles(kzv[u] * z, d);             // _calc_defocus   otf.py:357-360
-                        Dq[ii[u] * HP + jj[u]] = d;
-                        Dq[jj[u] * HP + ii[u]] = d;
-                    }
-                }
-            }
-        }
+        if constexpr (TAB) hanser_build_dtab<T, NT>(Dq, kzc, z, f0, K, tid);
         __syncthreads();
         // ---------------- fold + first column stage (registers), in place ----------------
         const T* __restrict__ amp = a.ampc + (size_t)v * KK;

@@ -1,0 +1,412 @@
+// K2: one phase-retrieval iteration (Hanser 2003) = the loop body of retrieve_phase,
+// pyotf/phaseretrieval.py:95-130, as two kernels:
+//
+//   pr_plane_kernel   (one CTA per (z-plane, row residue r), the same decomposition as K1)
+//       pupil * defocus -> 2D inverse FFT (fold / columns / rows, all on chip)      :97  (model.PSFi)
+//       per output pixel: PSFi = |PSFa|^2, (data - PSFi)^2 accumulated for the MSE   :98,401-403
+//                         PSFa <- sqrt(max(data,0)) * PSFa / |PSFa|                  :120-122
+//       2D forward FFT of the same rows (rows / columns / unfold: the exact transpose of
+//       the inverse decomposition, evaluated only on the pupil support box)          :124
+//       * conj(defocus)  (= / defocus, |defocus| = 1 on the box)                     :126
+//       -> per-CTA partial pupil [K][K]  (no atomics: the sum is deterministic)
+//   pr_finalize_kernel
+//       mse[i], mse_diff[i], pupil_diff[i], convergence test                         :99-114
+//       new_pupil = mean_z(partials) * mask, optional phase-only projection          :127-130
+//       sum |old - new|^2 and sum |old|^2 for the next iteration's pupil_diff        :105
+//
+// The PSF plane never leaves the SM: HBM/L2 traffic per iteration is one read of `data`,
+// one read of the compact pupil per CTA and one write + one read of the partial pupils.
+#pragma once
+#include "hanser.cuh"
+
+namespace pyotf {
+
+struct PrState {
+    int stopped;        // set by the finalize kernel when a tolerance is met
+    int iters_run;      // number of entries of mse / mse_diff / pupil_diff that are valid
+    int final_is_next;  // 1: the loop ran out, the final pupil is one update past the last applied one
+    int pad;
+};
+
+template <typename T> struct PrPlaneArgs {
+    const double* kzc;          // [KR][K]
+    const cplx<T>* pupilc;      // [KR][K] current pupil (compact, zero padded rows)
+    const cplx<T>* tw;          // [N]
+    const double* z;            // [nz]
+    const T* data;              // [nz][N][N] measured stack, fftshift-ed like PSFi
+    cplx<T>* partial;           // [nz * R][K][K]
+    double* mse_part;           // [nz * R]
+    const PrState* state;
+    int K, KR, KP, f0, nz;
+};
+
+template <typename T, int N, int M, bool TAB>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pr_plane_kernel(PrPlaneArgs<T> a) {
+    using RP = FftPlan<N>;
+    using CP = FftPlan<M>;
+    using SM = HanserSmem<N, M, T>;
+    constexpr int NT = SM::NT;
+    constexpr int R = N / M;
+    if (a.state->stopped) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[NT / 32];
+    cplx<T>* tws = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* U = tws + N;
+    cplx<T>* EX = U + (size_t)M * a.KP;
+    cplx<T>* Dq = EX;                                            // aliases EX (disjoint phases)
+
+    const int tid = threadIdx.x;
+    const int r = blockIdx.x % R;
+    const int plane = blockIdx.x / R;
+    const int K = a.K, KP = a.KP, f0 = a.f0;
+    const double z = a.z[plane];
+    const cplx<T>* __restrict__ pupil = a.pupilc;
+    const double* __restrict__ kzc = a.kzc;
+
+    for (int i = tid; i < N; i += NT) tws[i] = a.tw[i];
+
+    const int g = tid % RP::G;
+    const int grp = tid / RP::G;
+    const T scale = (T)1.0 / ((T)N * (T)N);
+    cplx<T> twr[RP::R1];
+#pragma unroll
+    for (int c = 0; c < RP::R1; ++c) twr[c] = cscale(a.tw[(g * c) & (N - 1)], scale);
+
+    const int ncw = (K + 31) >> 5;
+    const int nrl = (NT / 32) / ncw;
+    const int kx = ((tid >> 5) % ncw) * 32 + (tid & 31);
+    const int rl = (tid >> 5) / ncw;
+    const bool colactive = rl < nrl && kx < K;
+
+    if constexpr (TAB) hanser_build_dtab<T, NT>(Dq, kzc, z, f0, K, tid);
+    __syncthreads();
+    // ---------------- inverse: fold + columns ----------------
+    {
+        constexpr int Q1 = CP::R1, L1 = CP::R2;
+        if (colactive) hanser_fold_cols<TAB, true, T, N, M, false>(U, tws, Dq, nullptr, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
+        if constexpr (L1 > 1) {
+            __syncthreads();
+            if (colactive) {
+                for (int c1 = rl; c1 < Q1; c1 += nrl) {
+                    cplx<T> x[L1];
+#pragma unroll
+                    for (int q = 0; q < L1; ++q) x[q] = U[(c1 * L1 + q) * KP + kx];
+                    fft_radix<1, L1>(x);
+#pragma unroll
+                    for (int q = 0; q < L1; ++q) U[(c1 * L1 + q) * KP + kx] = x[q];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---------------- rows: inverse FFT_N, magnitude replacement, forward FFT_N ----------------
+    double mse_acc = 0.0;
+    {
+        constexpr int R1 = RP::R1, L1 = RP::R2, G = RP::G, NG = SM::NG, PITCH = SM::PITCH;
+        constexpr int CL1 = CP::R2, CQ1 = CP::R1;
+        cplx<T>* ex = EX + (size_t)grp * SM::EXSZ;
+        const int ipos = g - f0;
+        const int ineg = g - f0 - N;
+        const T* const dplane = a.data + (size_t)plane * N * N;
+        for (int l = grp; l < M; l += NG) {
+            const int yp = (l / CL1) + CQ1 * (l % CL1);
+            const int ys = (R * yp + r + N / 2) & (N - 1);
+            cplx<T>* Ul = U + (size_t)l * KP;
+            const T* const drow = dplane + (size_t)ys * N;
+            cplx<T> x[R1];
+#pragma unroll
+            for (int q = 0; q < R1; ++q) {
+                if (L1 * q < N / 2) x[q] = (ipos + L1 * q < K) ? Ul[ipos + L1 * q] : mk<T>(0, 0);
+                else x[q] = (ineg + L1 * q >= 0) ? Ul[ineg + L1 * q] : mk<T>(0, 0);
+            }
+            fft_radix<1, R1>(x);
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < R1; ++c) ex[c * PITCH + g] = cmul(x[c], twr[c]);
+            __syncwarp();
+            T macc = 0;
+            cplx<T> t[R1 / G][L1];
+#pragma unroll
+            for (int u = 0; u < R1 / G; ++u) {
+                const int c1 = g + G * u;
+                T dv[L1];
+#pragma unroll
+                for (int c2 = 0; c2 < L1; ++c2)                  // data is stored fftshift-ed
+                    dv[c2] = drow[(c1 + R1 * c2 + N / 2) & (N - 1)];
+#pragma unroll
+                for (int q = 0; q < L1; ++q) t[u][q] = ex[c1 * PITCH + q];
+                fft_radix<1, L1>(t[u]);                          // PSFa at x = c1 + R1*c2 (unshifted)
+#pragma unroll
+                for (int c2 = 0; c2 < L1; ++c2) {
+                    const T I = t[u][c2].x * t[u][c2].x + t[u][c2].y * t[u][c2].y;   // model PSFi
+                    const T d = dv[c2] - I;
+                    macc += d * d;                               // _calc_mse  phaseretrieval.py:401-403
+                    const T m = sqrt(fmax(dv[c2], (T)0));        // psqrt(data)  :79
+                    if (I > (T)0) {
+                        const T s = m / sqrt(I);                 // mag * exp(i angle(PSFa))  :120-122
+                        t[u][c2] = cscale(t[u][c2], s);
+                    } else {
+                        t[u][c2] = mk<T>(m, 0);                  // angle(0) = 0
+                    }
+                }
+            }
+            mse_acc += (double)macc;
+            // forward FFT_N over x (fftn(ifftshift(new_psf)): the registers already hold the unshifted order)
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < R1 / G; ++u) {
+                const int c1 = g + G * u;
+                fft_radix<-1, L1>(t[u]);                         // over c2 -> g'
+#pragma unroll
+                for (int q = 0; q < L1; ++q)
+                    ex[c1 * PITCH + q] = q ? cmulc(t[u][q], tws[(c1 * q) & (N - 1)]) : t[u][q];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < R1; ++c) x[c] = ex[c * PITCH + g];
+            fft_radix<-1, R1>(x);                                // over c1 -> q ; k = L1*q + g
+#pragma unroll
+            for (int q = 0; q < R1; ++q) {
+                if (L1 * q < N / 2) { if (ipos + L1 * q < K) Ul[ipos + L1 * q] = x[q]; }
+                else { if (ineg + L1 * q >= 0) Ul[ineg + L1 * q] = x[q]; }
+            }
+        }
+    }
+    __syncthreads();
+    // ---------------- forward columns: FFT_M over y' (transpose of the inverse stages) ----------------
+    {
+        constexpr int Q1 = CP::R1, L1 = CP::R2, JMAX = N / L1;
+        if constexpr (TAB) hanser_build_dtab<T, NT>(Dq, kzc, z, f0, K, tid);   // EX is free again
+        if constexpr (L1 > 1) {
+            if (colactive) {
+                for (int c1 = rl; c1 < Q1; c1 += nrl) {
+                    cplx<T> x[L1];
+#pragma unroll
+                    for (int q = 0; q < L1; ++q) x[q] = U[(c1 * L1 + q) * KP + kx];
+                    fft_radix<-1, L1>(x);                        // over d -> b'
+#pragma unroll
+                    for (int q = 0; q < L1; ++q) U[(c1 * L1 + q) * KP + kx] = x[q];
+                }
+            }
+        }
+        __syncthreads();
+        if (colactive) {
+            const int fx = f0 + kx, ax = fx < 0 ? -fx : fx;
+            const int HP = 1 - f0;
+            cplx<T>* __restrict__ outp = a.partial + (size_t)blockIdx.x * K * K + kx;
+            for (int bp = rl; bp < L1; bp += nrl) {
+                const int iy0 = (bp - f0) & (L1 - 1);
+                const int m0 = (f0 + iy0 - bp) / L1;
+                cplx<T> xs[Q1];
+#pragma unroll
+                for (int c = 0; c < Q1; ++c) {
+                    xs[c] = U[(c * L1 + bp) * KP + kx];
+                    // stage twiddle w_M^{-b' c} and the cyclic shift by m0 bins (shift theorem)
+                    if (c > 0) xs[c] = cmulc(xs[c], tws[(bp * c * R + m0 * c * (N / Q1)) & (N - 1)]);
+                }
+                fft_radix<-1, Q1>(xs);                           // over c -> q ; slot u holds bin b' + L1*((m0+u) mod Q1)
+#pragma unroll
+                for (int jb = 0; jb < JMAX; jb += Q1) {
+                    if (iy0 + L1 * jb >= K) break;
+#pragma unroll
+                    for (int u = 0; u < Q1; ++u) {
+                        const int iy = iy0 + L1 * (jb + u);
+                        if (iy < K) {
+                            const int fy = f0 + iy;
+                            cplx<T> d;
+                            if constexpr (TAB) {
+                                const int ay = fy < 0 ? -fy : fy;
+                                d = Dq[ay * HP + ax];
+                            } else {
+                                cis_cycles(kzc[iy * K + kx] * z, d);
+                            }
+                            // unfold: residue-r share of bin fy is w_N^{-fy r} G_r[fy mod M]; then / defocus
+                            cplx<T> v = xs[u];
+                            if constexpr (R > 1) v = cmulc(v, tws[(fy * r) & (N - 1)]);
+                            outp[(size_t)iy * K] = cmulc(v, d);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ---------------- block reduction of the squared error ----------------
+    for (int o = 16; o; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = mse_acc;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < NT / 32; ++w) s += red[w];
+        a.mse_part[blockIdx.x] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// reductions / update
+// ---------------------------------------------------------------------------------------
+// sums[p] = sum over parts of partial[part][p] (double), sums[KK] = (sum of mse parts, 0):
+// the buffer a z-sharded run all-reduces across ranks.
+template <typename T>
+__global__ void pr_reduce_kernel(const cplx<T>* __restrict__ partial, const double* __restrict__ mse_part, int nparts,
+                                 int KK, double2* __restrict__ sums, const PrState* __restrict__ state) {
+    if (state->stopped) return;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < KK) {
+        double sx = 0.0, sy = 0.0;
+        for (int q = 0; q < nparts; ++q) {
+            cplx<T> v = partial[(size_t)q * KK + p];
+            sx += (double)v.x; sy += (double)v.y;
+        }
+        sums[p] = make_double2(sx, sy);
+    }
+    if (p == KK) {
+        double s = 0.0;
+        for (int q = 0; q < nparts; ++q) s += mse_part[q];
+        sums[KK] = make_double2(s, 0.0);
+    }
+}
+
+struct PrFinalArgs {
+    int iter, K, nparts;
+    int cur;                // which pupil buffer holds the pupil this iteration applied
+    int phase_only, last_iter;
+    double npix_total;      // nz_total * N * N   (mean of the squared error)
+    double nz_total;        // planes over all ranks (mean over z of the new pupils)
+    double pupil_tol, mse_tol;
+};
+
+// deterministic warp sum of v[0], v[stride], ... (n terms): same order in every CTA
+__device__ __forceinline__ double warp_sum_fixed(const double* __restrict__ v, int n, int stride, int lane) {
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += v[(size_t)i * stride];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+constexpr int PR_FIN_PIX = 32;      // pixels per finalize CTA
+constexpr int PR_FIN_LANES = 8;     // threads sharing one pixel's sum over the partials
+
+// TP = cplx<T> (per-CTA partials of this rank) or double2 (all-reduced sums: nparts = 1 and
+// the squared-error numerator sits at index KK).  Block = 256 threads = 32 pixels x 8 part lanes.
+template <typename T, typename TP>
+__global__ void __launch_bounds__(256) pr_finalize_kernel(PrFinalArgs a, const TP* __restrict__ partial,
+                                                          const double* __restrict__ mse_part,
+                                                          const unsigned char* __restrict__ mask,
+                                                          cplx<T>* __restrict__ pupil0, cplx<T>* __restrict__ pupil1,
+                                                          double* __restrict__ diffpart /* [2][nblk][2] */,
+                                                          double* __restrict__ mse, double* __restrict__ mse_diff,
+                                                          double* __restrict__ pupil_diff, PrState* __restrict__ state) {
+    __shared__ double2 red[PR_FIN_LANES][PR_FIN_PIX];
+    __shared__ int s_stop;
+    const int tid = threadIdx.x;
+    const int px = tid & (PR_FIN_PIX - 1), lane = tid / PR_FIN_PIX;
+    const int KK = a.K * a.K;
+    if (state->stopped) return;
+    // every CTA evaluates the scalars in the same fixed order, so all of them take the same branch
+    if (tid < 32) {
+        double s;
+        if (a.nparts == 0) s = reinterpret_cast<const double2*>(partial)[KK].x;
+        else s = warp_sum_fixed(mse_part, a.nparts, 1, tid);
+        const double new_mse = s / a.npix_total;
+        double md = nan(""), pd = nan("");
+        if (a.iter > 0) {
+            const double old_mse = mse[a.iter - 1];
+            md = fabs(old_mse - new_mse) / old_mse;                    // phaseretrieval.py:103
+            const double* dp = diffpart + (size_t)(a.iter & 1) * 2 * gridDim.x;
+            const double num = warp_sum_fixed(dp, gridDim.x, 2, tid);
+            const double den = warp_sum_fixed(dp + 1, gridDim.x, 2, tid);
+            pd = num / den;                                            // :105
+        }
+        const int stop = (pd < a.pupil_tol) || (md < a.mse_tol) || (new_mse < a.mse_tol);   // :114
+        if (tid == 0) {
+            s_stop = stop;
+            if (blockIdx.x == 0) {
+                mse[a.iter] = new_mse; mse_diff[a.iter] = md; pupil_diff[a.iter] = pd;
+                state->iters_run = a.iter + 1;
+                if (stop) { state->final_is_next = 0; state->stopped = 1; }
+                else if (a.last_iter) state->final_is_next = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (s_stop) return;
+    const cplx<T>* __restrict__ oldp = a.cur ? pupil1 : pupil0;
+    cplx<T>* __restrict__ newp = a.cur ? pupil0 : pupil1;
+    const int p = blockIdx.x * PR_FIN_PIX + px;
+    double sx = 0.0, sy = 0.0;
+    if (p < KK) {
+        if (a.nparts == 0) {
+            if (lane == 0) { const double2 v = reinterpret_cast<const double2*>(partial)[p]; sx = v.x; sy = v.y; }
+        } else {
+            const cplx<T>* __restrict__ pp = reinterpret_cast<const cplx<T>*>(partial) + p;
+#pragma unroll 4
+            for (int q = lane; q < a.nparts; q += PR_FIN_LANES) {
+                const cplx<T> v = pp[(size_t)q * KK];
+                sx += (double)v.x; sy += (double)v.y;
+            }
+        }
+    }
+    red[lane][px] = make_double2(sx, sy);
+    __syncthreads();
+    if (tid < 32) {
+        double num = 0.0, den = 0.0;
+        if (p < KK) {
+            sx = 0.0; sy = 0.0;
+#pragma unroll
+            for (int l = 0; l < PR_FIN_LANES; ++l) { sx += red[l][px].x; sy += red[l][px].y; }
+            const double m = mask[p] ? 1.0 : 0.0;
+            sx = sx / a.nz_total * m; sy = sy / a.nz_total * m;        // mean(0) * mask   :127
+            if (a.phase_only) {                                        // exp(i angle(.)) * mask   :130
+                const double mag = hypot(sx, sy);
+                if (mag > 0.0) { sx = sx / mag * m; sy = sy / mag * m; }
+                else { sx = m; sy = 0.0; }
+            }
+            const cplx<T> o = oldp[p];
+            const cplx<T> nv = mk<T>((T)sx, (T)sy);
+            newp[p] = nv;
+            const double dx = (double)o.x - (double)nv.x, dy = (double)o.y - (double)nv.y;
+            num = dx * dx + dy * dy;
+            den = (double)o.x * (double)o.x + (double)o.y * (double)o.y;
+        }
+        for (int o = 16; o; o >>= 1) {
+            num += __shfl_xor_sync(0xffffffffu, num, o);
+            den += __shfl_xor_sync(0xffffffffu, den, o);
+        }
+        if (tid == 0) {
+            double* dp = diffpart + (size_t)((a.iter + 1) & 1) * 2 * gridDim.x;
+            dp[2 * blockIdx.x] = num; dp[2 * blockIdx.x + 1] = den;
+        }
+    }
+}
+
+// initial pupil = ideal mask as complex ones (HanserPSF._gen_pupil, otf.py:346-355), both buffers' padding zeroed
+template <typename T>
+__global__ void pr_init_pupil_kernel(const unsigned char* __restrict__ mask, int KKP, cplx<T>* __restrict__ p0,
+                                     cplx<T>* __restrict__ p1) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= KKP) return;
+    p0[i] = mk<T>(mask[i] ? (T)1 : (T)0, 0);
+    p1[i] = mk<T>(0, 0);
+}
+
+// measured stack (float32 or float64, any of the two) -> T
+template <typename TS, typename T>
+__global__ void pr_convert_data_kernel(const TS* __restrict__ src, T* __restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (T)src[i];
+}
+
+// compact [KR][K] pupil (T) -> unshifted N x N complex128 (zero outside the box)
+template <typename T>
+__global__ void pr_unpack_pupil_kernel(int N, int K, int f0, const cplx<T>* __restrict__ src, double2* __restrict__ dst) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * N) return;
+    int y = idx / N, x = idx - y * N;
+    int fy = y < N / 2 ? y : y - N, fx = x < N / 2 ? x : x - N;
+    int iy = fy - f0, ix = fx - f0;
+    double2 v = make_double2(0.0, 0.0);
+    if (iy >= 0 && iy < K && ix >= 0 && ix < K) { cplx<T> s = src[iy * K + ix]; v = make_double2((double)s.x, (double)s.y); }
+    dst[idx] = v;
+}
+
+}  // namespace pyotf

@@ -1,0 +1,216 @@
+// Host side of K2 (instantiated per dtype in pr_f32.cu / pr_f64.cu): state allocation, the
+// iteration loop of retrieve_phase (pyotf/phaseretrieval.py:95-135) as back-to-back kernel
+// launches with the convergence test on the device, and the optional z-sharded all-reduce.
+#pragma once
+#include "common.cuh"
+#include "pr.cuh"
+
+namespace pyotf {
+
+template <typename T> size_t pr_smem_for(int N, int M, int KP, int ntab) {
+    switch (N) {
+        case 32:  return hanser_smem_for<T, 32>(M, KP, ntab);
+        case 64:  return hanser_smem_for<T, 64>(M, KP, ntab);
+        case 128: return hanser_smem_for<T, 128>(M, KP, ntab);
+        default:  return hanser_smem_for<T, 256>(M, KP, ntab);
+    }
+}
+
+// rows per CTA: the largest M that lets two CTAs share an SM; fewer rows (more CTAs) when the
+// stack is too short to fill the GPU otherwise.
+template <typename T> int pr_pick_rows(const pyotf_hanser* h, int nz, int smem_limit, int sm_count, int want) {
+    const int ntab = hanser_ntab<T>(h);
+    const int cand[3] = {64, 32, 16};
+    if (want) {
+        for (int i = 0; i < 3; ++i)
+            if (cand[i] == want && want <= h->N && pr_smem_for<T>(h->N, want, h->KP, ntab) <= (size_t)smem_limit) return want;
+        return 0;
+    }
+    int pick = 0;
+    for (int pass = 0; pass < 2 && !pick; ++pass)
+        for (int i = 0; i < 3 && !pick; ++i) {
+            int M = cand[i];
+            if (M > h->N) continue;
+            size_t lim = pass == 0 ? (size_t)(smem_limit / 2 - 1024) : (size_t)smem_limit;
+            if (pr_smem_for<T>(h->N, M, h->KP, ntab) <= lim) pick = M;
+        }
+    while (pick > 32 && nz * (h->N / pick) < sm_count) pick /= 2;
+    return pick;
+}
+
+template <typename T, int N, int M, bool TAB>
+int pr_plane_launch_nmt(const PrPlaneArgs<T>& a, size_t smem, cudaStream_t s) {
+    auto kern = pr_plane_kernel<T, N, M, TAB>;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    kern<<<(unsigned)((N / M) * a.nz), 256, smem, s>>>(a);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int N, int M>
+int pr_plane_launch_nm(const pyotf_hanser* h, const PrPlaneArgs<T>& a, cudaStream_t s) {
+    int ntab = hanser_ntab<T>(h);
+    size_t smem = HanserSmem<N, M, T>::bytes(a.KP, ntab);
+    return ntab ? pr_plane_launch_nmt<T, N, M, true>(a, smem, s) : pr_plane_launch_nmt<T, N, M, false>(a, smem, s);
+}
+
+template <typename T, int N> int pr_plane_launch_n(const pyotf_hanser* h, int M, const PrPlaneArgs<T>& a, cudaStream_t s) {
+    if (M == 64) { if constexpr (N >= 64) return pr_plane_launch_nm<T, N, 64>(h, a, s); }
+    if (M == 32) { if constexpr (N >= 32) return pr_plane_launch_nm<T, N, 32>(h, a, s); }
+    return pr_plane_launch_nm<T, N, 16>(h, a, s);
+}
+
+template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, cudaStream_t st) {
+    const pyotf_hanser* h = s->h;
+    PrPlaneArgs<T> a;
+    a.kzc = h->kzc; a.pupilc = (const cplx<T>*)s->pupil[cur]; a.tw = (const cplx<T>*)h->tw; a.z = s->z;
+    a.data = (const T*)s->data; a.partial = (cplx<T>*)s->partial; a.mse_part = s->mse_part; a.state = (const PrState*)s->state;
+    a.K = h->K; a.KR = h->KR; a.KP = h->KP; a.f0 = h->f0; a.nz = s->nz;
+    switch (h->N) {
+        case 32:  return pr_plane_launch_n<T, 32>(h, s->M, a, st);
+        case 64:  return pr_plane_launch_n<T, 64>(h, s->M, a, st);
+        case 128: return pr_plane_launch_n<T, 128>(h, s->M, a, st);
+        case 256: return pr_plane_launch_n<T, 256>(h, s->M, a, st);
+        default: break;
+    }
+    set_error("pr: size must be one of 32, 64, 128, 256 on the fused path");
+    return 1;
+}
+
+template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype, int want_rows, cudaStream_t st) {
+    pyotf_hanser* h = s->h;
+    int smem_limit = 0, sms = 0;
+    PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    PYOTF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    s->M = pr_pick_rows<T>(h, s->nz, smem_limit, sms, want_rows);
+    PYOTF_REQUIRE(s->M != 0, "pr_create: no rows-per-CTA choice fits shared memory at this size / dtype");
+    s->nparts = s->nz * (h->N / s->M);
+    const size_t KK = (size_t)h->K * h->K, KKP = (size_t)h->KR * h->K, npix = (size_t)s->nz * h->N * h->N;
+    s->nblk = (int)((KK + PR_FIN_PIX - 1) / PR_FIN_PIX);
+    PYOTF_CUDA_OK(cudaMalloc(&s->data, npix * sizeof(T)));
+    PYOTF_CUDA_OK(cudaMalloc(&s->pupil[0], KKP * sizeof(cplx<T>)));
+    PYOTF_CUDA_OK(cudaMalloc(&s->pupil[1], KKP * sizeof(cplx<T>)));
+    PYOTF_CUDA_OK(cudaMalloc(&s->partial, (size_t)s->nparts * KK * sizeof(cplx<T>)));
+    PYOTF_CUDA_OK(cudaMalloc(&s->mse_part, (size_t)s->nparts * sizeof(double)));
+    PYOTF_CUDA_OK(cudaMalloc(&s->sums, (KK + 1) * sizeof(double2)));
+    PYOTF_CUDA_OK(cudaMalloc(&s->diffpart, (size_t)4 * s->nblk * sizeof(double)));
+    PYOTF_CUDA_OK(cudaMalloc(&s->state, sizeof(PrState)));
+    PYOTF_CUDA_OK(cudaMemsetAsync(s->state, 0, sizeof(PrState), st));
+    const unsigned nb = (unsigned)((npix + 255) / 256);
+    if (data_dtype == PYOTF_F32) pr_convert_data_kernel<float, T><<<nb, 256, 0, st>>>((const float*)data, (T*)s->data, npix);
+    else pr_convert_data_kernel<double, T><<<nb, 256, 0, st>>>((const double*)data, (T*)s->data, npix);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    pr_init_pupil_kernel<T><<<(unsigned)((KKP + 255) / 256), 256, 0, st>>>(h->maskc, (int)KKP, (cplx<T>*)s->pupil[0],
+                                                                          (cplx<T>*)s->pupil[1]);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    s->cur = 0; s->applied = 0;
+    return 0;
+}
+
+template <typename T> int pr_set_pupil(pyotf_pr* s, const void* pupil_c128, cudaStream_t st) {
+    const pyotf_hanser* h = s->h;
+    const size_t KKP = (size_t)h->KR * h->K;
+    if (!pupil_c128) {
+        pr_init_pupil_kernel<T><<<(unsigned)((KKP + 255) / 256), 256, 0, st>>>(h->maskc, (int)KKP, (cplx<T>*)s->pupil[0],
+                                                                              (cplx<T>*)s->pupil[1]);
+        PYOTF_CUDA_OK(cudaGetLastError());
+        s->cur = 0; s->applied = 0;
+        return 0;
+    }
+    int rc = hanser_pack<T>(h, pupil_c128, 1, s->pupil[s->cur], st);
+    s->applied = s->cur;
+    return rc;
+}
+
+template <typename T> int pr_get_pupil(const pyotf_pr* s, int which, void* out_c128, cudaStream_t st) {
+    const pyotf_hanser* h = s->h;
+    const int n = h->N * h->N;
+    pr_unpack_pupil_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(h->N, h->K, h->f0,
+                                                              (const cplx<T>*)s->pupil[which ? s->applied : s->cur],
+                                                              (double2*)out_c128);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int comm_allreduce_f64(pyotf_comm* c, double* buf, long long n, cudaStream_t st);
+
+template <typename T>
+int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int phase_only, pyotf_comm* comm,
+           double* mse_host, double* mse_diff_host, double* pupil_diff_host, int* iters_run_host, cudaStream_t st) {
+    const pyotf_hanser* h = s->h;
+    const int KK = h->K * h->K;
+    if (s->cap_iters < max_iters) {
+        cudaFree(s->mse); cudaFree(s->mse_diff); cudaFree(s->pupil_diff);
+        s->mse = s->mse_diff = s->pupil_diff = nullptr; s->cap_iters = 0;
+        PYOTF_CUDA_OK(cudaMalloc(&s->mse, sizeof(double) * max_iters));
+        PYOTF_CUDA_OK(cudaMalloc(&s->mse_diff, sizeof(double) * max_iters));
+        PYOTF_CUDA_OK(cudaMalloc(&s->pupil_diff, sizeof(double) * max_iters));
+        s->cap_iters = max_iters;
+    }
+    constexpr int CHK = 8, NSLOT = 4;
+    if (!s->h_flags) {
+        PYOTF_CUDA_OK(cudaMallocHost(&s->h_flags, sizeof(int) * NSLOT));
+        for (int i = 0; i < NSLOT; ++i) PYOTF_CUDA_OK(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
+    }
+    PYOTF_CUDA_OK(cudaMemsetAsync(s->state, 0, sizeof(PrState), st));
+    PrFinalArgs fa;
+    fa.K = h->K; fa.phase_only = phase_only;
+    fa.npix_total = (double)s->nz_total * h->N * h->N; fa.nz_total = (double)s->nz_total;
+    fa.pupil_tol = pupil_tol; fa.mse_tol = mse_tol;
+    const int start = s->cur;
+    int launched = 0;
+    for (int i = 0; i < max_iters; ++i) {
+        if (i % CHK == 0 && i >= 2 * CHK) {            // stay at most ~2*CHK iterations ahead of the device
+            const int slot = (i / CHK - 2) % NSLOT;
+            PYOTF_CUDA_OK(cudaEventSynchronize(s->ev[slot]));
+            if (s->h_flags[slot]) break;
+        }
+        const int cur = (start + i) & 1;
+        int rc = pr_plane_launch<T>(s, cur, st);
+        if (rc) return rc;
+        fa.iter = i; fa.cur = cur; fa.last_iter = i == max_iters - 1;
+        if (comm) {
+            pr_reduce_kernel<T><<<(KK + 1 + 255) / 256, 256, 0, st>>>((const cplx<T>*)s->partial, s->mse_part, s->nparts, KK,
+                                                                     (double2*)s->sums, (const PrState*)s->state);
+            PYOTF_CUDA_OK(cudaGetLastError());
+            rc = comm_allreduce_f64(comm, (double*)s->sums, 2ll * (KK + 1), st);
+            if (rc) return rc;
+            fa.nparts = 0;
+            pr_finalize_kernel<T, double2><<<s->nblk, 256, 0, st>>>(fa, (const double2*)s->sums, s->mse_part, h->maskc,
+                                                                   (cplx<T>*)s->pupil[0], (cplx<T>*)s->pupil[1], s->diffpart,
+                                                                   s->mse, s->mse_diff, s->pupil_diff, (PrState*)s->state);
+        } else {
+            fa.nparts = s->nparts;
+            pr_finalize_kernel<T, cplx<T>><<<s->nblk, 256, 0, st>>>(fa, (const cplx<T>*)s->partial, s->mse_part, h->maskc,
+                                                                   (cplx<T>*)s->pupil[0], (cplx<T>*)s->pupil[1], s->diffpart,
+                                                                   s->mse, s->mse_diff, s->pupil_diff, (PrState*)s->state);
+        }
+        PYOTF_CUDA_OK(cudaGetLastError());
+        ++launched;
+        if (i % CHK == CHK - 1) {
+            const int slot = (i / CHK) % NSLOT;
+            PYOTF_CUDA_OK(cudaMemcpyAsync(&s->h_flags[slot], &((PrState*)s->state)->stopped, sizeof(int),
+                                          cudaMemcpyDeviceToHost, st));
+            PYOTF_CUDA_OK(cudaEventRecord(s->ev[slot], st));
+        }
+    }
+    PrState hs;
+    PYOTF_CUDA_OK(cudaMemcpyAsync(&hs, s->state, sizeof(PrState), cudaMemcpyDeviceToHost, st));
+    PYOTF_CUDA_OK(cudaStreamSynchronize(st));
+    const int n = hs.iters_run;
+    PYOTF_REQUIRE(n >= 1 && n <= launched, "pr_run: inconsistent device state");
+    s->applied = (start + n - 1) & 1;                  // the pupil iteration n-1 applied   (result.model)
+    s->cur = hs.stopped ? s->applied : (s->applied ^ 1);   // final new_pupil                  :144-148
+    s->launched = launched;
+    if (mse_host) PYOTF_CUDA_OK(cudaMemcpy(mse_host, s->mse, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (mse_diff_host) PYOTF_CUDA_OK(cudaMemcpy(mse_diff_host, s->mse_diff, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (pupil_diff_host) PYOTF_CUDA_OK(cudaMemcpy(pupil_diff_host, s->pupil_diff, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (iters_run_host) *iters_run_host = n;
+    return 0;
+}
+
+}  // namespace pyotf

@@ -1,0 +1,87 @@
+// Host-side 2D phase unwrapping (Herraez, Burton, Lalor, Gdeisat, Appl. Opt. 41, 7437 (2002)):
+// reliability-sorted path following with a weighted union-find.  Stand-in for
+// skimage.restoration.unwrap_phase at pyotf/phaseretrieval.py:146 (an un-vendored dependency
+// of the reference).  It post-processes ONE N x N pupil after the GPU loop has finished
+// (SURVEY.md section 8f row N2); the algorithm is a serial sort + union-find, so it runs on
+// the host exactly like the reference's.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+constexpr double PI = 3.14159265358979323846;
+inline double wrap(double x) { return x > PI ? x - 2 * PI : (x < -PI ? x + 2 * PI : x); }
+inline int jump(double a, double b) { double d = a - b; return d > PI ? 1 : (d < -PI ? -1 : 0); }
+
+struct UnionFind {
+    std::vector<int> parent, size, pot;   // pot[p] = n[p] - n[parent[p]] in units of 2 pi
+    explicit UnionFind(int n) : parent(n), size(n, 1), pot(n, 0) { std::iota(parent.begin(), parent.end(), 0); }
+    std::vector<int> path;
+    int find(int p, int& acc) {           // returns root, acc = n[p] - n[root]; compresses the path
+        path.clear();
+        int cur = p;
+        while (parent[cur] != cur) { path.push_back(cur); cur = parent[cur]; }
+        const int root = cur;
+        int total = 0;
+        for (int i = (int)path.size() - 1; i >= 0; --i) {   // from the node next to the root outwards
+            const int node = path[i];
+            total += pot[node];
+            pot[node] = total;
+            parent[node] = root;
+        }
+        acc = total;
+        return root;
+    }
+};
+}  // namespace
+
+extern "C" int pyotf_b200_unwrap_phase_2d(const double* in, double* out, int ny, int nx) {
+    PYOTF_REQUIRE(in && out && ny > 0 && nx > 0, "unwrap_phase_2d: bad argument");
+    const int n = ny * nx;
+    std::vector<double> v(n), rel(n);
+    for (int i = 0; i < n; ++i) v[i] = wrap(in[i]);   // already in [-pi, pi] for np.angle output
+    for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x) {
+            const int i = y * nx + x;
+            if (y == 0 || x == 0 || y == ny - 1 || x == nx - 1) {
+                rel[i] = 1e7 + (double)((uint32_t)i * 2654435761u >> 8);    // borders last, deterministic order
+                continue;
+            }
+            const double c = v[i];
+            const double H = wrap(v[i - 1] - c) - wrap(c - v[i + 1]);
+            const double V = wrap(v[i - nx] - c) - wrap(c - v[i + nx]);
+            const double D1 = wrap(v[i - nx - 1] - c) - wrap(c - v[i + nx + 1]);
+            const double D2 = wrap(v[i - nx + 1] - c) - wrap(c - v[i + nx - 1]);
+            rel[i] = H * H + V * V + D1 * D1 + D2 * D2;
+        }
+    struct Edge { double r; int a, b; };
+    std::vector<Edge> edges;
+    edges.reserve((size_t)2 * n);
+    for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x) {
+            const int i = y * nx + x;
+            if (x + 1 < nx) edges.push_back({rel[i] + rel[i + 1], i, i + 1});
+            if (y + 1 < ny) edges.push_back({rel[i] + rel[i + nx], i, i + nx});
+        }
+    std::stable_sort(edges.begin(), edges.end(), [](const Edge& p, const Edge& q) { return p.r < q.r; });
+    UnionFind uf(n);
+    for (const Edge& e : edges) {
+        int pa, pb;
+        const int ra = uf.find(e.a, pa), rb = uf.find(e.b, pb);
+        if (ra == rb) continue;
+        const int d = jump(v[e.a], v[e.b]);            // n[b] - n[a] that makes the pair continuous
+        const int nrb_minus_nra = d + pa - pb;
+        if (uf.size[ra] > uf.size[rb]) { uf.parent[rb] = ra; uf.pot[rb] = nrb_minus_nra; uf.size[ra] += uf.size[rb]; }
+        else { uf.parent[ra] = rb; uf.pot[ra] = -nrb_minus_nra; uf.size[rb] += uf.size[ra]; }
+    }
+    for (int i = 0; i < n; ++i) {
+        int acc;
+        uf.find(i, acc);
+        out[i] = v[i] + 2 * PI * (double)acc;
+    }
+    return 0;
+}
