@@ -155,6 +155,93 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def fixture_stack():
+    """BASELINE config 2 input: the reference's measured 25 x 256^2 stack (committed losslessly under
+    tests/golden/), background-subtracted exactly like the reference's demo (prep_data_for_PR(data, 256, 1.1))."""
+    from pyotf_b200.utils import prep_data_for_PR
+
+    raw = np.load(os.path.join(ROOT, "tests", "golden", "fixture_psf_520.npz"))["raw"]
+    return prep_data_for_PR(raw, 256, 1.1)
+
+
+PR_PARAMS = dict(wl=520, na=0.85, ni=1.0, res=130, zres=300)
+
+
+def cpu_baseline_pr(iters=8):
+    """Oracle port of retrieve_phase's loop on the fixture stack, `iters` iterations, one core."""
+    from oracle import pyotf_oracle as orc
+
+    data = fixture_stack()
+    t0 = time.perf_counter()
+    orc.retrieve_phase_loop(data, PR_PARAMS["wl"], PR_PARAMS["na"], PR_PARAMS["ni"], PR_PARAMS["res"],
+                            zres=PR_PARAMS["zres"], max_iters=iters, pupil_tol=0, mse_tol=0)
+    dt = time.perf_counter() - t0
+    return {"value": iters / dt, "unit": "iters/s", "cores": 1, "kind": "port",
+            "sample": f"oracle/pyotf_oracle.py retrieve_phase_loop on the 25 x 256^2 fixture stack, {iters} iterations "
+                      f"in {dt:.1f} s (numpy/pocketfft complex128, 1 of {os.cpu_count()} cores)"}
+
+
+def bench_pr(precision, rank, world, dist, reps=5, iters=100):
+    """Phase-retrieval iterations/s on BASELINE config 2 (fixture stack, 100 iterations, tolerances 0 so
+    that exactly 100 run).  With N ranks the 25 planes are z-sharded (strong scaling) and every iteration
+    all-reduces the partial pupil sums over NCCL."""
+    import torch
+
+    from pyotf_b200 import _engine as eng
+    from pyotf_b200.phaseretrieval import retrieve_phase
+
+    data = fixture_stack()
+    nz_total = data.shape[0]
+    lo, hi = eng.shard_bounds(nz_total, rank, world)
+    zall = (np.arange(nz_total) - (nz_total + 1) // 2) * PR_PARAMS["zres"]
+    comm = eng.Comm(rank, world) if world > 1 else None
+    dt = np.float32 if precision == "fp32" else np.float64
+    dloc = torch.as_tensor(np.ascontiguousarray(data[lo:hi].astype(dt)), device="cuda")
+    st = eng.PRState(PR_PARAMS["wl"], PR_PARAMS["na"], PR_PARAMS["ni"], PR_PARAMS["res"], 256, zall[lo:hi], dloc,
+                     precision, nz_total=nz_total)
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    times = []
+    for rep in range(reps + 2):
+        st.set_pupil(None)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        mse, _, _ = st.run(iters, 0.0, 0.0, comm=comm)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        if rep >= 2:
+            times.append(ms)
+    assert len(mse) == iters
+    best = min(times)
+    out = {"iters_per_s": iters / (best * 1e-3), "us_per_iter": 1e3 * best / iters,
+           "us_per_iter_median": 1e3 * float(np.median(times)) / iters, "iters": iters, "n_gpus": world,
+           "scaling": "strong", "dtype": "f32" if precision == "fp32" else "f64",
+           "workload": "retrieve_phase on the 25 x 256^2 fixture stack, 100 iterations, tol 0 (BASELINE config 2)",
+           "rows_per_cta": st.rows_per_cta, "ctas_per_iteration": st.nparts,
+           "kernels_per_iteration": 2 if world == 1 else 4, "final_mse": float(mse[-1]),
+           "parallelism": f"z-shard x{world}" + ("" if world == 1 else " + 1 NCCL all-reduce / iteration")}
+    if world == 1:
+        # end to end through the public API: host stack in, PhaseRetrievalResult (host arrays) out
+        params = dict(PR_PARAMS)
+        retrieve_phase(data, dict(params), iters, 0, 0, precision=precision)
+        t0 = time.perf_counter()
+        r = retrieve_phase(data, dict(params), iters, 0, 0, precision=precision)
+        dt_s = time.perf_counter() - t0
+        out["e2e"] = {"iters_per_s": iters / dt_s, "ms_total": 1e3 * dt_s, "h2d_bytes": int(data.nbytes),
+                      "d2h_bytes": int(r.pupil.nbytes + 3 * 8 * iters),
+                      "path": "retrieve_phase(host ndarray) -> PhaseRetrievalResult incl. host unwrap"}
+    if comm is not None:
+        comm.close()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
@@ -252,6 +339,10 @@ def run_ours(args):
         e2e_s = float(t.item())
     assert p.shape == (nz, N, N)
 
+    pr = None
+    if not args.no_pr:
+        pr = bench_pr(precision, rank, world, dist)
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         alg_bytes = nz * N * N * esize  # N^2 * s_r per plane -> PSFi only
@@ -283,8 +374,13 @@ def run_ours(args):
                     "path": "HanserPSF.zrange = host array; HanserPSF.PSFi -> numpy (pinned D2H)"},
             "gpu_launches": args.steps,
         }
+        if pr is not None:
+            line["phase_retrieval"] = pr
+            line["gpu_launches"] = args.steps   # timed region of `value`; the PR leg launches 2 kernels / iteration
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_hanser()
+            if pr is not None:
+                pr["cpu_baseline"] = cpu_baseline_pr()
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -300,6 +396,7 @@ def main():
     ap.add_argument("--workload", default="hanser256")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-pr", action="store_true", help="skip the phase-retrieval leg")
     ap.add_argument("--min-seconds", type=float, default=1.0,
                     help="repeat the K-step measurement for at least this long (clock sampling); 0 = once")
     args = ap.parse_args()

@@ -107,6 +107,26 @@ int pyotf_b200_hanser_aberration_pupil(const pyotf_hanser_t* h, const int* n_dev
                                        void* pupilc_out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * SheppardPSF  (pyotf/otf.py:446-592)
+ * ---------------------------------------------------------------------------------- */
+typedef struct pyotf_sheppard_params {
+    double wl, na, ni, res, zres;
+    int size, zsize;        /* N (x/y) and number of kz planes; any positive sizes */
+    int vec_corr;           /* PYOTF_VEC_* */
+    int condition;          /* PYOTF_COND_* (ignored by the scalar model, otf.py:577-579) */
+    int dual;               /* 0 | 1: mirrored cap (otf.py:525-529) */
+    int dtype;              /* PYOTF_F32 / PYOTF_F64 */
+} pyotf_sheppard_params;
+
+/* K3 generator -- SheppardPSF._gen_kr + _gen_otf (otf.py:497-582).
+ *   otfa_out_dev  NULL or [nvec][zsize][size][size] complex, fftshift-ed (== SheppardPSF.OTFa)
+ *   valid_out_dev NULL or [zsize][size][size] uint8, UNSHIFTED (== SheppardPSF.valid_points)
+ * PSFa = pyotf_b200_fftn(OTFa, axes (1,2,3), inverse, shift_in, shift_out)  (otf.py:589-592);
+ * PSFi = pyotf_b200_abs2_sum0(PSFa)                                         (otf.py:204-207). */
+int pyotf_b200_sheppard_otfa(const pyotf_sheppard_params* params, void* otfa_out_dev, unsigned char* valid_out_dev,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Phase retrieval  (pyotf/phaseretrieval.py:32-149, the loop :95-135, _calc_mse :401-403)
  * ---------------------------------------------------------------------------------- */
 typedef struct pyotf_pr pyotf_pr_t;

@@ -326,13 +326,38 @@ def aberration_pupil(handle, n, m, mcoefs, pcoefs):
     return out
 
 
+_pinned_pool = []          # [pinned tensor, weakref to the numpy view handed out]
+_PINNED_POOL_MAX = 8
+
+
+def _pinned_like(t):
+    """(slot) with a pinned host tensor of t's shape/dtype.  cudaHostAlloc costs milliseconds for a 32 MiB
+    stack, so a buffer is recycled once the numpy array handed out for it (and every view of it) is gone."""
+    torch = _torch()
+    with _handles_lock:
+        for i, slot in enumerate(_pinned_pool):
+            buf, ref = slot
+            if buf.dtype == t.dtype and buf.shape == t.shape and (ref is None or ref() is None):
+                _pinned_pool.append(_pinned_pool.pop(i))
+                return slot
+        slot = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True), None]
+        _pinned_pool.append(slot)
+        while len(_pinned_pool) > _PINNED_POOL_MAX:
+            _pinned_pool.pop(0)
+        return slot
+
+
 def to_host(t):
-    """CUDA tensor -> numpy array through a pinned staging buffer (the array owns the buffer)."""
+    """CUDA tensor -> numpy array through a pinned staging buffer (the array keeps the buffer alive)."""
+    import weakref
+
     torch = _torch()
     t = t.detach()
     if not t.is_cuda:
         return t.numpy()
-    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    host.copy_(t, non_blocking=True)
+    slot = _pinned_like(t)
+    slot[0].copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return host.numpy()
+    arr = slot[0].numpy()
+    slot[1] = weakref.ref(arr)
+    return arr

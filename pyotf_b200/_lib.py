@@ -18,6 +18,14 @@ class HanserParams(C.Structure):
     ]
 
 
+class SheppardParams(C.Structure):
+    _fields_ = [
+        ("wl", C.c_double), ("na", C.c_double), ("ni", C.c_double), ("res", C.c_double), ("zres", C.c_double),
+        ("size", C.c_int), ("zsize", C.c_int), ("vec_corr", C.c_int), ("condition", C.c_int), ("dual", C.c_int),
+        ("dtype", C.c_int),
+    ]
+
+
 class Pyotf_b200Error(RuntimeError):
     """Raised when a C-ABI entry point reports an error."""
 
@@ -44,6 +52,7 @@ PROTOTYPES = {
     "pyotf_b200_fftn": (_i, [_vp, _vp, _i, C.POINTER(_ll), _ip, _i, _i, _i, _i, _i, _i, _vp]),
     "pyotf_b200_abs2_sum0": (_i, [_vp, _i, _ll, _vp, _i, _vp]),
     "pyotf_b200_hanser_aberration_pupil": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "pyotf_b200_sheppard_otfa": (_i, [C.POINTER(SheppardParams), _vp, _vp, _vp]),
     "pyotf_b200_pr_create": (_i, [C.POINTER(HanserParams), _vp, _i, _ll, _vp, _i, _i, _vp, C.POINTER(_vp)]),
     "pyotf_b200_pr_destroy": (_i, [_vp]),
     "pyotf_b200_pr_info": (_i, [_vp, _ip, _ip, _ip, _ip, _ip]),

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "hanser.cuh"
 #include "zernike.cuh"
+#include "sheppard.cuh"
 
 namespace pyotf {
 static thread_local std::string g_last_error;
@@ -181,6 +182,35 @@ int pyotf_b200_hanser_aberration_pupil(const pyotf_hanser_t* h, const int* n, co
     cudaStream_t s = (cudaStream_t)stream;
     return h->p.dtype == PYOTF_F32 ? aberration_launch<float>(h, n, m, nmodes, mc, pc, batch, out, s)
                                    : aberration_launch<double>(h, n, m, nmodes, mc, pc, batch, out, s);
+}
+
+int pyotf_b200_sheppard_otfa(const pyotf_sheppard_params* q, void* otfa, unsigned char* valid, void* stream) {
+    PYOTF_REQUIRE(q && (otfa || valid), "sheppard_otfa: null argument");
+    PYOTF_REQUIRE(q->wl > 0 && q->na > 0 && q->ni > 0 && q->res > 0 && q->zres > 0, "sheppard_otfa: wl, na, ni, res, zres must be positive");
+    PYOTF_REQUIRE(q->size > 0 && q->zsize > 0 && q->zsize <= 65535 && q->size <= 65535, "sheppard_otfa: bad size");
+    PYOTF_REQUIRE(q->vec_corr >= 0 && q->vec_corr <= 4 && q->condition >= 0 && q->condition <= 2, "sheppard_otfa: bad enum");
+    PYOTF_REQUIRE(q->dtype == PYOTF_F32 || q->dtype == PYOTF_F64, "sheppard_otfa: bad dtype");
+    SheppardParams p;
+    p.N = q->size; p.NZ = q->zsize; p.vec_mode = q->vec_corr; p.condition = q->condition; p.dual = q->dual ? 1 : 0;
+    p.nvec = q->vec_corr == PYOTF_VEC_NONE ? 1 : (q->vec_corr == PYOTF_VEC_TOTAL ? 6 : 2);
+    p.kstep = 1.0 / ((double)q->size * q->res);          // numpy.fft.fftfreq: val = 1.0 / (n * d)
+    p.kzstep = 1.0 / ((double)q->zsize * q->zres);
+    // dk = k[1] - k[0] (otf.py:508); a length-1 axis has no k[1]: the reference raises IndexError there
+    PYOTF_REQUIRE(q->size > 1 && q->zsize > 1, "sheppard_otfa: size and zsize must be > 1");
+    p.dk = (q->size == 2 ? -1.0 : 1.0) * p.kstep;          // fftfreq(2) = [0, -1] * val
+    p.dkz = (q->zsize == 2 ? -1.0 : 1.0) * p.kzstep;
+    p.same_dk = p.dk == p.dkz;
+    p.kmag = q->ni / q->wl;
+    const double nawl = q->na / q->wl;
+    const double arg = p.kmag * p.kmag - nawl * nawl;      // otf.py:512
+    PYOTF_REQUIRE(arg >= 0, "sheppard_otfa: na > ni");
+    p.kz_min = sqrt(arg);
+    dim3 grid((unsigned)((q->size + 255) / 256), (unsigned)q->size, (unsigned)q->zsize);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (q->dtype == PYOTF_F32) sheppard_otf_kernel<float><<<grid, 256, 0, s>>>(p, (cplx<float>*)otfa, valid);
+    else sheppard_otf_kernel<double><<<grid, 256, 0, s>>>(p, (cplx<double>*)otfa, valid);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev, int nz, long long nz_total,

@@ -1,0 +1,17 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, the bench line, the ncu launch list and full captures of the two
+# hot kernels.  Usage (from the repo root, under gpurun):  bash tools/gpu_round.sh <tag>
+set -u
+TAG=${1:-r1}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_$TAG.log
+python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err; cat gpurun_out/bench_ref_$TAG.json
+python tools/prof_cmd.py k1 pr > gpurun_out/plain_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
+    python tools/prof_cmd.py k1 pr > gpurun_out/ncu_launch_$TAG.log 2>&1
+echo "launch list rc=$?"
+python tools/prof_cmd.py k1 pr > gpurun_out/plain_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'hanser_psf_kernel|pr_plane_kernel|pr_finalize' -c 6 -f \
+    -o gpurun_out/hot_$TAG python tools/prof_cmd.py k1 pr > gpurun_out/ncu_full_$TAG.log 2>&1
+echo "full capture rc=$?"

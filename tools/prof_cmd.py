@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Short driver for ncu captures: a few launches of each hot kernel on the BASELINE shapes.
+
+    python tools/prof_cmd.py [k1] [pr] [otf] [sheppard] [--precision fp32|fp64]
+
+k1: HanserPSF cfg1 (256^2 x 128 planes -> PSFi), 4 launches.   pr: retrieve_phase loop on the fixture
+stack, 6 iterations.  Numbers printed by this script under ncu are NOT bench values.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+
+    from pyotf_b200 import _engine as eng
+
+    what = [a for a in sys.argv[1:] if not a.startswith("--")] or ["k1", "pr"]
+    precision = "fp64" if "--precision=fp64" in sys.argv else "fp32"
+    torch.cuda.set_device(0)
+    if "k1" in what:
+        h = eng.hanser_handle(520, 0.85, 1.0, 130, 256, "none", "sine", precision, -1)
+        z = eng.to_device_f64((np.arange(128) - 64) * 300.0)
+        for _ in range(4):
+            _, psfi = h.psf(z)
+        torch.cuda.synchronize()
+        print("k1 ok", float(psfi.sum()))
+    if "pr" in what:
+        sys.path.insert(0, ROOT)
+        import bench
+
+        data = bench.fixture_stack()
+        dt = np.float32 if precision == "fp32" else np.float64
+        zall = (np.arange(25) - 13) * 300.0
+        st = eng.PRState(520, 0.85, 1.0, 130, 256, zall, torch.as_tensor(data.astype(dt), device="cuda"), precision)
+        mse, _, _ = st.run(6, 0.0, 0.0)
+        print("pr ok", mse[-1])
+    if "otf" in what:
+        from pyotf_b200.otf import HanserPSF
+
+        m = HanserPSF(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=256, zsize=128, precision=precision)
+        o = m.OTFi_dev
+        torch.cuda.synchronize()
+        print("otf ok", float(o.abs().max()))
+    if "sheppard" in what:
+        from pyotf_b200.otf import SheppardPSF
+
+        m = SheppardPSF(wl=520, na=1.27, ni=1.33, res=100, zres=190, size=256, zsize=256, precision=precision)
+        p = m.PSFi_dev
+        torch.cuda.synchronize()
+        print("sheppard ok", float(p.sum()))
+
+
+if __name__ == "__main__":
+    main()
