@@ -48,7 +48,7 @@ int pyotf_b200_device_query(int device, int* sm_count, int* smem_optin_bytes, in
 int pyotf_b200_hanser_create(const pyotf_hanser_params* p, void* stream, pyotf_hanser_t** out) {
     PYOTF_REQUIRE(p && out, "hanser_create: null argument");
     PYOTF_REQUIRE(p->wl > 0 && p->na > 0 && p->ni > 0 && p->res > 0, "hanser_create: wl, na, ni, res must be positive");
-    PYOTF_REQUIRE(is_pow2(p->size) && p->size >= 32, "hanser_create: size must be a power of two >= 32");
+    PYOTF_REQUIRE(p->size >= 2 && p->size <= 16384, "hanser_create: size must be in 2..16384");
     PYOTF_REQUIRE(p->vec_corr >= 0 && p->vec_corr <= 4, "hanser_create: bad vec_corr");
     PYOTF_REQUIRE(p->condition >= 0 && p->condition <= 2, "hanser_create: bad condition");
     PYOTF_REQUIRE(p->dtype == PYOTF_F32 || p->dtype == PYOTF_F64, "hanser_create: bad dtype");
@@ -112,7 +112,7 @@ int pyotf_b200_hanser_tables(const pyotf_hanser_t* h, double* kz_dev, void* amp_
 
 int pyotf_b200_pupil_support(const void* pupil, int size, int* hmax_host, void* stream) {
     PYOTF_REQUIRE(pupil && hmax_host, "pupil_support: null argument");
-    PYOTF_REQUIRE(is_pow2(size), "pupil_support: size must be a power of two");
+    PYOTF_REQUIRE(size >= 2, "pupil_support: bad size");
     cudaStream_t s = (cudaStream_t)stream;
     int* d = nullptr;
     PYOTF_CUDA_OK(cudaMallocAsync(&d, sizeof(int), s));
@@ -218,7 +218,8 @@ int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev,
     PYOTF_REQUIRE(params && z_dev && data_dev && out, "pr_create: null argument");
     PYOTF_REQUIRE(nz > 0 && nz_total >= nz, "pr_create: bad nz / nz_total");
     PYOTF_REQUIRE(data_dtype == PYOTF_F32 || data_dtype == PYOTF_F64, "pr_create: bad data dtype");
-    PYOTF_REQUIRE(params->size <= 256, "pr_create: size must be one of 32, 64, 128, 256 on the fused path");
+    PYOTF_REQUIRE(params->size == 32 || params->size == 64 || params->size == 128 || params->size == 256,
+                  "pr_create: size must be one of 32, 64, 128, 256 on the fused path");
     pyotf_hanser_params p = *params;
     p.vec_corr = PYOTF_VEC_NONE; p.condition = PYOTF_COND_NONE; p.support = -2;   // phaseretrieval.py:74-76
     pyotf_pr* s = new pyotf_pr();

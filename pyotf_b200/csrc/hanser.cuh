@@ -58,7 +58,7 @@ __global__ void hanser_geometry_kernel(HanserGeomParams p, double* __restrict__ 
     }
     double ky = __dmul_rn((double)(p.f0 + iy), p.kstep);
     double kx = __dmul_rn((double)(p.f0 + ix), p.kstep);
-    double kr = hypot(ky, kx);                                  // cart2pol(kyy, kxx)  utils.py:25-29
+    double kr = hypot_ref(ky, kx);                                  // cart2pol(kyy, kxx)  utils.py:25-29
     double phi = atan2(ky, kx);
     double kz2 = __dsub_rn(__dmul_rn(p.kmag, p.kmag), __dmul_rn(kr, kr));
     double kz = sqrt(fmax(0.0, kz2));                           // psqrt              otf.py:344
@@ -109,7 +109,7 @@ __global__ void pack_pupil_kernel(int N, int K, int KR, int f0, const double2* _
     int b = idx / KK, r = idx - b * KK;
     int iy = r / K, ix = r - iy * K;
     if (iy >= K) { dst[idx] = mk<T>(0, 0); return; }
-    int y = (f0 + iy) & (N - 1), x = (f0 + ix) & (N - 1);
+    int y = ((f0 + iy) % N + N) % N, x = ((f0 + ix) % N + N) % N;       // fftfreq order, any N
     double2 v = src[(size_t)b * N * N + (size_t)y * N + x];
     dst[idx] = mk<T>((T)v.x, (T)v.y);
 }

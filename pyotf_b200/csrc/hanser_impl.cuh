@@ -1,7 +1,10 @@
 // Per-dtype host launchers for K1 (instantiated in hanser_f32.cu / hanser_f64.cu).
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 #include "hanser.cuh"
+#include "hanser_big.cuh"
 
 namespace pyotf {
 
@@ -86,6 +89,79 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int batch, in
     return hanser_launch_nm<T, N, 16>(h, a, batch, s);
 }
 
+// ---------------------------------------------------------------------------------------
+// K1b launchers (hanser_big.cuh): any size, two line-FFT passes per plane chunk
+// ---------------------------------------------------------------------------------------
+template <int DIR, typename T, int L, bool POW2, bool LM, int TI, class LD, class ST>
+int fft_lines_launch_ti(int Lr, long long nlines, LD ld, ST st, size_t smem, cudaStream_t s) {
+    auto kern = fft_lines_kernel<DIR, T, L, TI, POW2, LM, LD, ST>;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    long long nblocks = (nlines + TI - 1) / TI;
+    PYOTF_REQUIRE(nblocks > 0 && nblocks < (1ll << 31), "hanser_psf: bad grid");
+    kern<<<(unsigned)nblocks, 256, smem, s>>>(Lr, nlines, ld, st);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int DIR, typename T, int L, bool POW2, bool LM, class LD, class ST>
+int fft_lines_launch_l(int Lr, long long nlines, LD ld, ST st, int smem_limit, cudaStream_t s) {
+    auto need = [&](int ti) { return sizeof(cplx<T>) * ((size_t)Lr + (size_t)ti * (Lr + 1) * (POW2 ? 1 : 2)); };
+    const size_t soft = (size_t)smem_limit / 2 - 1024;
+    if (need(16) <= soft || (need(8) > (size_t)smem_limit && need(16) <= (size_t)smem_limit))
+        return fft_lines_launch_ti<DIR, T, L, POW2, LM, 16>(Lr, nlines, ld, st, need(16), s);
+    if (need(8) <= soft || (need(4) > (size_t)smem_limit && need(8) <= (size_t)smem_limit))
+        return fft_lines_launch_ti<DIR, T, L, POW2, LM, 8>(Lr, nlines, ld, st, need(8), s);
+    PYOTF_REQUIRE(need(4) <= (size_t)smem_limit, "hanser_psf: size too large for the shared-memory line FFT");
+    return fft_lines_launch_ti<DIR, T, L, POW2, LM, 4>(Lr, nlines, ld, st, need(4), s);
+}
+
+template <int DIR, typename T, bool LM, class LD, class ST>
+int fft_lines_launch(int L, long long nlines, LD ld, ST st, int smem_limit, cudaStream_t s) {
+    switch (L) {
+#define PYOTF_CASE(LL) case LL: return fft_lines_launch_l<DIR, T, LL, true, LM>(L, nlines, ld, st, smem_limit, s);
+        PYOTF_CASE(2) PYOTF_CASE(4) PYOTF_CASE(8) PYOTF_CASE(16) PYOTF_CASE(32) PYOTF_CASE(64) PYOTF_CASE(128)
+        PYOTF_CASE(256) PYOTF_CASE(512) PYOTF_CASE(1024) PYOTF_CASE(2048)
+#undef PYOTF_CASE
+        default: return fft_lines_launch_l<DIR, T, 0, false, LM>(L, nlines, ld, st, smem_limit, s);
+    }
+}
+
+template <typename T>
+int hanser_launch_big(const pyotf_hanser* h, const double* z, int nz, const void* pupilc, int batch,
+                      long long pupil_stride, void* psfa, void* psfi, int smem_limit, cudaStream_t s) {
+    const int N = h->N, K = h->K;
+    const size_t plane = (size_t)N * N, KKP = (size_t)h->KR * K;
+    // planes per chunk: keep the K x N intermediate of a chunk L2-resident (<= 48 MiB)
+    const size_t wplane = (size_t)K * N * sizeof(cplx<T>);
+    int nzc = (int)std::max<size_t>(1, std::min<size_t>((size_t)nz, ((size_t)48 << 20) / wplane));
+    cplx<T>* W = nullptr;
+    PYOTF_CUDA_OK(cudaMallocAsync(&W, wplane * nzc, s));
+    int rc = 0;
+    for (int b = 0; b < batch && !rc; ++b)
+        for (int z0 = 0; z0 < nz && !rc; z0 += nzc) {
+            const int nc = std::min(nzc, nz - z0);
+            for (int v = 0; v < h->nvec && !rc; ++v) {
+                BigArgs<T> a;
+                a.kzc = h->kzc; a.ampc = (const T*)h->ampc + (size_t)v * KKP;
+                a.pupilc = pupilc ? (const cplx<T>*)pupilc + (size_t)b * pupil_stride : nullptr;
+                a.pupil_stride = 0; a.z = z + z0; a.W = W;
+                a.psfa = psfa ? (cplx<T>*)psfa + (((size_t)b * h->nvec + v) * nz + z0) * plane : nullptr;
+                a.psfi = psfi ? (T*)psfi + ((size_t)b * nz + z0) * plane : nullptr;
+                a.psfa_bstride = 0; a.psfi_bstride = 0;
+                a.N = N; a.K = K; a.f0 = h->f0; a.nzc = nc; a.accumulate = v > 0;
+                a.scale = 1.0 / ((double)N * (double)N);           // numpy ifftn "backward" normalisation
+                rc = fft_lines_launch<1, T, true>(N, (long long)nc * K, BigRowLoad<T>{a}, BigRowStore<T>{a}, smem_limit, s);
+                if (!rc) rc = fft_lines_launch<1, T, false>(N, (long long)nc * N, BigColLoad<T>{a}, BigColStore<T>{a}, smem_limit, s);
+            }
+        }
+    cudaFreeAsync(W, s);
+    return rc;
+}
+
 template <typename T>
 int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pupilc, int batch,
                   long long pupil_stride, void* psfa, void* psfi, cudaStream_t s) {
@@ -102,8 +178,7 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
         case 256: return hanser_launch_n<T, 256>(h, a, batch, smem_limit, s);
         default: break;
     }
-    set_error("hanser_psf: size must be one of 32, 64, 128, 256 on the fused path");
-    return 1;
+    return hanser_launch_big<T>(h, z, nz, pupilc, batch, pupil_stride, psfa, psfi, smem_limit, s);
 }
 
 }  // namespace pyotf

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) aberration_pupil_kernel(AberrationParams 
             int iy = idx / p.K, ix = idx - iy * p.K;
             double ky = __dmul_rn((double)(p.f0 + iy), p.kstep);
             double kx = __dmul_rn((double)(p.f0 + ix), p.kstep);
-            double kr = hypot(ky, kx), phi = atan2(ky, kx);
+            double kr = hypot_ref(ky, kx), phi = atan2(ky, kx);
             double r = __dmul_rn(kr, p.wl) / p.na;              // otf.py:632
             val = zernike_value(r, phi, zn[j], zm[j], 1);
             if (j == 0) ideal[q] = kr <= p.diff_limit ? 1.0 : 0.0;
@@ -130,7 +130,7 @@ static __global__ void hanser_kspace_kernel(int N, double kstep, double kmag, do
     int y = idx / N, x = idx - y * N;
     int fy = y < (N + 1) / 2 ? y : y - N, fx = x < (N + 1) / 2 ? x : x - N;
     double ky = __dmul_rn((double)fy, kstep), kx = __dmul_rn((double)fx, kstep);
-    double kr = hypot(ky, kx);
+    double kr = hypot_ref(ky, kx);
     if (kr_out) kr_out[idx] = kr;
     if (phi_out) phi_out[idx] = atan2(ky, kx);
     if (kz_out) kz_out[idx] = sqrt(fmax(0.0, __dsub_rn(__dmul_rn(kmag, kmag), __dmul_rn(kr, kr))));

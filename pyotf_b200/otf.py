@@ -299,9 +299,8 @@ class HanserPSF(BasePSF):
     # -- K1 ---------------------------------------------------------------------------------
     def _check_size(self):
         n = self.size
-        if n & (n - 1) or n < 32:
-            raise NotImplementedError(
-                f"size={n}: the CUDA path needs a power-of-two size >= 32 (there is no CPU fallback)")
+        if n < 2 or n > 16384:
+            raise NotImplementedError(f"size={n}: the CUDA path covers sizes 2..16384 (there is no CPU fallback)")
 
     def _handle_and_pupil(self, pupil_base):
         """Resolve (HanserHandle, compact pupil tensor or None) for a pupil_base argument."""

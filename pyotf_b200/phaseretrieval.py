@@ -62,9 +62,9 @@ def retrieve_phase(data, params, max_iters=200, pupil_tol=1e-8, mse_tol=1e-8, ph
     assert data.ndim == 3, "Data doesn't have enough dims"
     params.update(dict(vec_corr="none", condition="none", zsize=data.shape[0], size=data.shape[-1]))
     model = HanserPSF(**params, precision=precision)
-    model._check_size()
-    if model.size > 256:
-        raise NotImplementedError("retrieve_phase: the fused CUDA path covers sizes 32..256 (no CPU fallback)")
+    if model.size not in (32, 64, 128, 256):
+        raise NotImplementedError("retrieve_phase: the fused CUDA path covers sizes 32, 64, 128 and 256 "
+                                  "(there is no CPU fallback)")
     torch = _engine._torch()
     want = torch.float32 if model.precision == "fp32" else torch.float64
     if not isinstance(data, np.ndarray) and hasattr(data, "is_cuda"):

@@ -100,7 +100,8 @@ def test_hooks_and_cache_semantics():
     m._gen_kr()
     k, kr, phi, kmag, kz = orc.hanser_kspace(520, 1.0, 130, 64)
     np.testing.assert_array_equal(m._k, k)
-    np.testing.assert_allclose(m._kr, kr, rtol=4e-16)
+    np.testing.assert_array_equal(m._kr, kr)          # bit-equal to numpy.hypot
+    np.testing.assert_array_equal(m._kz, kz)
     np.testing.assert_allclose(m._phi, phi, rtol=1e-15, atol=1e-16)
     assert m._kmag == kmag
     np.testing.assert_array_equal(m._gen_pupil(), orc.hanser_pupil(kr, 0.85, 520))

@@ -107,8 +107,8 @@ def test_geometry_tables_match_oracle():
         np.testing.assert_array_equal(mask.astype(bool), (kr <= na / wl)[sub])
         # nothing of the ideal pupil lies outside the compact box
         assert (kr <= na / wl).sum() == mask.sum()
-        # hypot is within 1 ulp of glibc's; kz = sqrt(kmag^2 - kr^2) amplifies that near kr -> kmag
-        np.testing.assert_allclose(kz, kz_ref[sub], rtol=1e-13, atol=8 * np.finfo(float).eps * kmag)
+        # kr is bit-equal to numpy.hypot (hypot_ref restates glibc's algorithm), hence so is kz
+        np.testing.assert_array_equal(kz, kz_ref[sub])
         theta = np.arcsin((kr < kmag) * kr / kmag)
         a = (1 / np.sqrt(np.cos(theta))) * (kr <= na / wl)
         np.testing.assert_allclose(amp[0], a[sub], rtol=1e-14)
