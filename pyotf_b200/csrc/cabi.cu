@@ -85,7 +85,7 @@ int pyotf_b200_hanser_create(const pyotf_hanser_params* p, void* stream, pyotf_h
 
 int pyotf_b200_hanser_destroy(pyotf_hanser_t* h) {
     if (!h) return 0;
-    cudaFree(h->kzc); cudaFree(h->ampc); cudaFree(h->maskc); cudaFree(h->tw);
+    cudaFree(h->kzc); cudaFree(h->ampc); cudaFree(h->maskc); cudaFree(h->tw); cudaFree(h->dtab);
     delete h;
     return 0;
 }
@@ -241,7 +241,7 @@ int pyotf_b200_pr_destroy(pyotf_pr_t* s) {
     if (!s) return 0;
     cudaFree(s->z); cudaFree(s->data); cudaFree(s->pupil[0]); cudaFree(s->pupil[1]); cudaFree(s->partial);
     cudaFree(s->mse_part); cudaFree(s->sums); cudaFree(s->diffpart); cudaFree(s->mse); cudaFree(s->mse_diff);
-    cudaFree(s->pupil_diff); cudaFree(s->state);
+    cudaFree(s->pupil_diff); cudaFree(s->state); cudaFree(s->dtab);
     if (s->h_flags) { cudaFreeHost(s->h_flags); for (int i = 0; i < 4; ++i) cudaEventDestroy(s->ev[i]); }
     pyotf_b200_hanser_destroy(s->h);
     delete s;

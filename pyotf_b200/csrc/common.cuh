@@ -39,6 +39,8 @@ struct pyotf_hanser {
     void* ampc = nullptr;           // [nvec*K*K] dtype
     unsigned char* maskc = nullptr; // [K*K]
     void* tw = nullptr;             // [N] complex dtype
+    void* dtab = nullptr;           // [planes][dtab_size] per-plane defocus tables (scratch, grown on demand)
+    size_t dtab_cap = 0;            // capacity of dtab in bytes
 };
 
 struct pyotf_comm;
@@ -46,7 +48,7 @@ struct pyotf_comm;
 // phase-retrieval state (K2); buffers are in the handle's dtype unless noted
 struct pyotf_pr {
     pyotf_hanser* h = nullptr;      // owned geometry (support = -2, vec_corr / condition = none)
-    int nz = 0, M = 0, nparts = 0, nblk = 0, cap_iters = 0;
+    int nz = 0, M = 0, nth = 256, nparts = 0, nblk = 0, cap_iters = 0;
     long long nz_total = 0;         // planes over all ranks of a z-sharded retrieval
     int cur = 0, applied = 0;       // pupil buffer holding the final / the last applied pupil
     int launched = 0;               // iterations enqueued by the last run
@@ -58,6 +60,7 @@ struct pyotf_pr {
     void* sums = nullptr;           // [K*K + 1] double2 (all-reduce buffer)
     double* diffpart = nullptr;     // [2][nblk][2]
     double *mse = nullptr, *mse_diff = nullptr, *pupil_diff = nullptr;   // [cap_iters]
+    void* dtab = nullptr;           // [nz][dtab_size] defocus tables of this stack (built once)
     void* state = nullptr;          // PrState
     int* h_flags = nullptr;         // pinned: early-stop polling
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

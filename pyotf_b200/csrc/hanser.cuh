@@ -135,6 +135,8 @@ template <typename T> struct HanserArgs {
     const T* ampc;            // [nvec][KR][K]
     const cplx<T>* pupilc;    // [B][KR][K] or nullptr
     const cplx<T>* tw;        // [N] e^{+2 pi i k/N}
+    const cplx<T>* dtab;      // [nz][dtab_size] per-plane defocus tables (TAB variants) or nullptr
+    int amp_in_tab;           // the tables already hold amp * D (ideal pupil, scalar model)
     const double* z;          // [nz]
     T* psfi;                  // [B][nz][N][N] or nullptr
     cplx<T>* psfa;            // [B][nvec][nz][N][N] or nullptr
@@ -142,51 +144,47 @@ template <typename T> struct HanserArgs {
     long long pupil_stride;   // elements between pupils in pupilc (0 = shared)
 };
 
-template <int N, int M, typename T> struct HanserSmem {
+template <int N, int M, typename T, int NTHREADS = 256> struct HanserSmem {
     using RP = FftPlan<N>;
-    static constexpr int NT = 256;
+    static constexpr int NT = NTHREADS;
     static constexpr int NG = NT / RP::G;                     // row groups per CTA
     static constexpr int PITCH = RP::R2 + 1;                  // exchange pitch (elements)
     static constexpr int EXSZ = ((RP::R1 * PITCH + 7) / 8) * 8 + (RP::G == 8 ? 8 : 0);
-    // the defocus table (fold phase) and the row-exchange buffers (row phase) share one region
-    __host__ __device__ static size_t bytes(int KP, int ntab) {
-        size_t ex = (size_t)NG * EXSZ;
-        return sizeof(cplx<T>) * ((size_t)N + (size_t)M * KP + (ex > (size_t)ntab ? ex : (size_t)ntab));
+    // twiddles + column/row work area U + the row-exchange buffers
+    __host__ __device__ static size_t bytes(int KP) {
+        return sizeof(cplx<T>) * ((size_t)N + (size_t)M * KP + (size_t)NG * EXSZ);
     }
 };
 
-// Quadrant table of the defocus factor: Dq[|fy|][|fx|] = exp(2 pi i kz(|fy|,|fx|) z), pitch H + 1.
-// kz depends on fy^2 + fx^2 only, so each octant entry (i >= j >= 0) is evaluated once
-// (HanserPSF._calc_defocus, pyotf/otf.py:357-360).
-template <typename T, int NT>
-__device__ __forceinline__ void hanser_build_dtab(cplx<T>* __restrict__ Dq, const double* __restrict__ kzc, double z,
-                                                  int f0, int K, int tid) {
-    const int H = -f0, HP = H + 1, ntri = (H + 1) * (H + 2) / 2;
-    for (int e0 = tid; e0 < ntri; e0 += 4 * NT) {
-        double kzv[4];
-        int ii[4], jj[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {                  // issue the four loads before any sincos
-            const int e = e0 + u * NT;
-            ii[u] = -1; jj[u] = 0; kzv[u] = 0.0;
-            if (e < ntri) {
-                int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-                if (i * (i + 1) / 2 > e) --i;
-                if ((i + 1) * (i + 2) / 2 <= e) ++i;
-                ii[u] = i; jj[u] = e - i * (i + 1) / 2;
-                kzv[u] = kzc[(H + i) * K + (H + jj[u])];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (ii[u] >= 0) {
-                cplx<T> d;
-                cis_cycles(kzv[u] * z, d);
-                Dq[ii[u] * HP + jj[u]] = d;
-                Dq[jj[u] * HP + ii[u]] = d;
-            }
-        }
-    }
+// Quadrant tables of the defocus factor, one per plane, in global memory (L2 / L1 resident):
+//   dtab[plane][|fy|][|fx|] = exp(2 pi i kz(|fy|,|fx|) z[plane])   (* amp when `amp` is given: the scalar
+//   model's apodisation is radially symmetric too), row pitch dtab_pitch(f0).
+// kz depends on fy^2 + fx^2 only, so each octant entry (i >= j >= 0) is evaluated once and mirrored
+// (HanserPSF._calc_defocus, pyotf/otf.py:357-360).  The phase kz*z (hundreds of cycles) is formed and
+// reduced in fp64.  One tiny launch per stack serves every CTA of every batch entry; phase retrieval
+// builds its tables once per measured stack.  Entries are dealt to threads by row pairs (rows p and
+// H-p hold H+2 octant entries together), which keeps the index decode integer-only.
+__host__ __device__ __forceinline__ int dtab_pitch(int f0) { return (1 - f0) | 1; }
+__host__ __device__ __forceinline__ int dtab_size(int f0) { return (1 - f0) * dtab_pitch(f0); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) hanser_dtab_kernel(const double* __restrict__ kzc, const T* __restrict__ amp,
+                                                          const double* __restrict__ zr, int f0, int K,
+                                                          cplx<T>* __restrict__ dtab) {
+    const int H = -f0, HP = dtab_pitch(f0), W = H + 2, ntot = (H / 2 + 1) * W;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ntot) return;
+    const int p = e / W, t = e - p * W;
+    int i, j;
+    if (t <= p) { i = p; j = t; } else { i = H - p; j = t - p - 1; }
+    if (t > p && i == p) return;                       // the middle row of an even H is its own partner
+    const unsigned o = (unsigned)((H + i) * K + (H + j));
+    cplx<T> d;
+    cis_cycles(kzc[o] * zr[blockIdx.y], d);
+    if (amp) d = cscale(d, amp[o]);
+    cplx<T>* __restrict__ tab = dtab + (size_t)blockIdx.y * dtab_size(f0);
+    tab[i * HP + j] = d;
+    tab[j * HP + i] = d;
 }
 
 // Fold fused with the first column-FFT stage, for one thread's column kx and sub-row bp.
@@ -196,19 +194,25 @@ __device__ __forceinline__ void hanser_build_dtab(cplx<T>* __restrict__ Dq, cons
 // cyclic offset m0 is repaid after the butterfly as the phase w_Q1^{m0 c} (shift theorem),
 // merged into the stage twiddle.  Each group of Q1 rows is branch-free (clamped address,
 // zero weight when out of range) so its global loads issue back to back.
-template <bool TAB, bool HASP, typename T, int N, int M, bool AMP = true>
+// what multiplies the defocus factor in the fold
+enum FoldMode {
+    FOLD_TAB_ONLY = 0,    // nothing: the table already holds amp * D      (ideal pupil, scalar model)
+    FOLD_AMP = 1,         // amp                                           (ideal pupil, vectorial components)
+    FOLD_PUPIL_AMP = 2,   // pupil * amp                                   (user / aberrated pupil)
+    FOLD_PUPIL = 3        // pupil                                         (phase retrieval: unit apodisation)
+};
+
+template <bool TAB, int PM, typename T, int N, int M>
 __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const cplx<T>* __restrict__ tws,
                                                  const cplx<T>* __restrict__ Dq, const T* __restrict__ amp,
                                                  const cplx<T>* __restrict__ pupil, const double* __restrict__ kzc,
                                                  double z, int K, int KP, int f0, int r, int kx, int rl, int nrl) {
     using CP = FftPlan<M>;
     constexpr int R = N / M, Q1 = CP::R1, L1 = CP::R2, JMAX = N / L1;
+    static_assert(TAB || PM != FOLD_TAB_ONLY, "FOLD_TAB_ONLY needs the table");
     const int fx = f0 + kx, ax = fx < 0 ? -fx : fx;
-    const int HP = 1 - f0;                                       // table pitch H + 1
-    const unsigned rowstride = (unsigned)K;
-    const T* __restrict__ ap = amp + kx;
-    const cplx<T>* __restrict__ pp = pupil + kx;
-    const double* __restrict__ kzp = kzc + kx;
+    const int H = -f0, HP = dtab_pitch(f0);
+    const cplx<T>* __restrict__ dcol = Dq + ax;
     // rot[t] = w_R^{t r}: phase between consecutive groups of Q1 rows (they are M rows apart)
     cplx<T> rot[R];
 #pragma unroll
@@ -216,6 +220,10 @@ __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const 
     for (int bp = rl; bp < L1; bp += nrl) {
         const int iy0 = (bp - f0) & (L1 - 1);
         const int m0 = (f0 + iy0 - bp) / L1;                      // exact
+        // one 32-bit element index serves every table (uniform base + index: one IMAD.WIDE per load)
+        unsigned idx = (unsigned)(iy0 * K + kx);
+        const unsigned step = (unsigned)(L1 * K);
+        int fy = f0 + iy0;
         cplx<T> xs[Q1];
 #pragma unroll
         for (int q = 0; q < Q1; ++q) xs[q] = mk<T>(0, 0);
@@ -224,26 +232,25 @@ __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const 
             if (iy0 + L1 * jb >= K) break;                        // warp-uniform
 #pragma unroll
             for (int u = 0; u < Q1; ++u) {
-                // rows >= K read the zero padding of the tables (KR = K + M rows), no clamp needed
-                const int iy = iy0 + L1 * (jb + u);
-                const int fy = f0 + iy;
-                const unsigned off = (unsigned)iy * rowstride;
+                // rows >= K read the zero padding of the amp / pupil tables (KR = K + 64 rows)
                 cplx<T> d;
                 if constexpr (TAB) {
                     int ay = fy < 0 ? -fy : fy;
-                    ay = ay < HP ? ay : HP - 1;                   // keep the lookup inside the table
-                    d = Dq[ay * HP + ax];
+                    ay = ay < H ? ay : H;                         // padded rows: any in-table entry will do
+                    d = dcol[ay * HP];
                 } else {
-                    cis_cycles(kzp[off] * z, d);                   // _calc_defocus   otf.py:357-360
+                    cis_cycles(kzc[idx] * z, d);                   // _calc_defocus   otf.py:357-360
                 }
                 cplx<T> p;
-                if constexpr (AMP) {
-                    const T am = ap[off];
-                    if constexpr (HASP) p = cmul(cscale(pp[off], am), d);
-                    else p = cscale(d, am);
-                } else {                                          // unit apodisation (phase retrieval)
-                    static_assert(HASP || AMP, "a pupil or an amplitude table is required");
-                    p = cmul(pp[off], d);
+                if constexpr (PM == FOLD_TAB_ONLY) {
+                    p = d;
+                    if (fy > H) p = mk<T>(0, 0);                  // warp-uniform: past the last pupil row
+                } else if constexpr (PM == FOLD_AMP) {
+                    p = cscale(d, amp[idx]);
+                } else if constexpr (PM == FOLD_PUPIL_AMP) {
+                    p = cmul(cscale(pupil[idx], amp[idx]), d);
+                } else {
+                    p = cmul(pupil[idx], d);
                 }
                 // w_N^{fy r} = w_N^{(bp + L1 (m0 + u)) r} * w_R^{(jb / Q1) r}: the second factor is
                 // CTA-uniform per group, the first is applied once per slot after the loop
@@ -253,6 +260,8 @@ __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const 
                     xs[u].x += p.x * w.x - p.y * w.y;
                     xs[u].y += p.x * w.y + p.y * w.x;
                 }
+                idx += step;
+                fy += L1;
             }
         }
         if constexpr (R > 1) {
@@ -283,12 +292,12 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
     cplx<T>* tws = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* U = tws + N;
     cplx<T>* EX = U + (size_t)M * a.KP;
-    cplx<T>* Dq = EX;                                            // aliases EX (disjoint phases)
 
     const int tid = threadIdx.x;
     const int r = blockIdx.x % R;
     const int plane = blockIdx.x / R;
     const int bidx = blockIdx.y;
+    const cplx<T>* __restrict__ Dq = TAB ? a.dtab + (size_t)plane * dtab_size(a.f0) : nullptr;
     const int K = a.K, KP = a.KP, f0 = a.f0, KK = a.KR * K;
     const double z = a.z[plane];
     const cplx<T>* __restrict__ pupil = a.pupilc ? a.pupilc + (size_t)bidx * a.pupil_stride : nullptr;
@@ -315,15 +324,16 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
 
     for (int v = 0; v < a.nvec; ++v) {
         __syncthreads();                                         // previous component's rows are done with EX
-        if constexpr (TAB) hanser_build_dtab<T, NT>(Dq, kzc, z, f0, K, tid);
-        __syncthreads();
-        // ---------------- fold + first column stage (registers), in place ----------------
+        // scalar model + ideal pupil: the (radially symmetric) apodisation rides in the defocus table
+        const bool tab_only = TAB && a.amp_in_tab;
         const T* __restrict__ amp = a.ampc + (size_t)v * KK;
+        // ---------------- fold + first column stage (registers), in place ----------------
         {
             constexpr int Q1 = CP::R1, L1 = CP::R2;
             if (colactive) {
-                if (pupil) hanser_fold_cols<TAB, true, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
-                else hanser_fold_cols<TAB, false, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
+                if (pupil) hanser_fold_cols<TAB, FOLD_PUPIL_AMP, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
+                else if (TAB && tab_only) hanser_fold_cols<TAB, TAB ? FOLD_TAB_ONLY : FOLD_AMP, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
+                else hanser_fold_cols<TAB, FOLD_AMP, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
             }
             if constexpr (L1 > 1) {
                 __syncthreads();

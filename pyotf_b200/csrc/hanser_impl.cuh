@@ -33,11 +33,21 @@ int hanser_pack(const pyotf_hanser* h, const void* src, int batch, void* dst, cu
     return 0;
 }
 
-// octant table entries when the support box is symmetric and the table is small, else 0
+// entries of one per-plane defocus table when the support box is symmetric about DC, else 0
 template <typename T> int hanser_ntab(const pyotf_hanser* h) {
     if (h->K != 2 * (-h->f0) + 1) return 0;
-    int H = -h->f0, ntab = (H + 1) * (H + 1);     // quadrant table [|fy|][|fx|]
-    return (size_t)ntab * sizeof(cplx<T>) <= 48 * 1024 ? ntab : 0;
+    return dtab_size(h->f0);
+}
+
+// (re)build the per-plane defocus tables of a stack into `dst` ([nz][ntab])
+template <typename T>
+int hanser_build_dtabs(const pyotf_hanser* h, const double* z, int nz, bool with_amp, cplx<T>* dst, cudaStream_t s) {
+    const int H = -h->f0, ntot = (H / 2 + 1) * (H + 2);
+    PYOTF_REQUIRE(nz <= 65535, "hanser_psf: too many planes for one launch");
+    dim3 grid((unsigned)((ntot + 255) / 256), (unsigned)nz);
+    hanser_dtab_kernel<T><<<grid, 256, 0, s>>>(h->kzc, with_amp ? (const T*)h->ampc : nullptr, z, h->f0, h->K, dst);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 template <typename T, int N, int M, bool TAB>
@@ -57,16 +67,15 @@ int hanser_launch_nmt(const HanserArgs<T>& a, int batch, size_t smem, cudaStream
 
 template <typename T, int N, int M>
 int hanser_launch_nm(const pyotf_hanser* h, const HanserArgs<T>& a, int batch, cudaStream_t s) {
-    int ntab = hanser_ntab<T>(h);
-    size_t smem = HanserSmem<N, M, T>::bytes(a.KP, ntab);
-    return ntab ? hanser_launch_nmt<T, N, M, true>(a, batch, smem, s)
-                : hanser_launch_nmt<T, N, M, false>(a, batch, smem, s);
+    size_t smem = HanserSmem<N, M, T>::bytes(a.KP);
+    return a.dtab ? hanser_launch_nmt<T, N, M, true>(a, batch, smem, s)
+                  : hanser_launch_nmt<T, N, M, false>(a, batch, smem, s);
 }
 
-template <typename T, int N> size_t hanser_smem_for(int M, int KP, int ntab) {
-    if (M == 16) return HanserSmem<N, 16, T>::bytes(KP, ntab);
-    if (M == 32) return HanserSmem<N, (N >= 32 ? 32 : 16), T>::bytes(KP, ntab);
-    return HanserSmem<N, (N >= 64 ? 64 : 16), T>::bytes(KP, ntab);
+template <typename T, int N> size_t hanser_smem_for(int M, int KP) {
+    if (M == 16) return HanserSmem<N, 16, T>::bytes(KP);
+    if (M == 32) return HanserSmem<N, (N >= 32 ? 32 : 16), T>::bytes(KP);
+    return HanserSmem<N, (N >= 64 ? 64 : 16), T>::bytes(KP);
 }
 
 template <typename T, int N>
@@ -74,12 +83,11 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int batch, in
     // largest rows-per-CTA M whose working set allows two CTAs per SM, else the largest that fits
     int pick = 0;
     const int cand[3] = {64, 32, 16};
-    const int ntab = hanser_ntab<T>(h);
     for (int pass = 0; pass < 2 && !pick; ++pass)
         for (int i = 0; i < 3 && !pick; ++i) {
             int M = cand[i];
             if (M > N) continue;
-            size_t need = hanser_smem_for<T, N>(M, a.KP, ntab);
+            size_t need = hanser_smem_for<T, N>(M, a.KP);
             size_t lim = pass == 0 ? (size_t)(smem_limit / 2 - 1024) : (size_t)smem_limit;
             if (need <= lim) pick = M;
         }
@@ -171,6 +179,24 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
     a.K = h->K; a.KR = h->KR; a.KP = h->KP; a.f0 = h->f0; a.nz = nz; a.nvec = h->nvec; a.pupil_stride = pupil_stride;
     int smem_limit = 0;
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    a.dtab = nullptr; a.amp_in_tab = 0;
+    const int ntab = hanser_ntab<T>(h);
+    if (ntab && (h->N == 32 || h->N == 64 || h->N == 128 || h->N == 256)) {
+        // per-plane defocus tables (one small launch per stack); the handle owns the scratch.
+        // NOTE: a handle must not be used from two streams at once (the scratch is shared).
+        pyotf_hanser* hm = const_cast<pyotf_hanser*>(h);
+        const size_t need = (size_t)nz * ntab * sizeof(cplx<T>);
+        if (need > hm->dtab_cap) {
+            PYOTF_CUDA_OK(cudaStreamSynchronize(s));
+            cudaFree(hm->dtab); hm->dtab = nullptr; hm->dtab_cap = 0;
+            PYOTF_CUDA_OK(cudaMalloc(&hm->dtab, need));
+            hm->dtab_cap = need;
+        }
+        a.amp_in_tab = (!pupilc && h->nvec == 1) ? 1 : 0;
+        int rc = hanser_build_dtabs<T>(h, z, nz, a.amp_in_tab != 0, (cplx<T>*)hm->dtab, s);
+        if (rc) return rc;
+        a.dtab = (const cplx<T>*)hm->dtab;
+    }
     switch (h->N) {
         case 32:  return hanser_launch_n<T, 32>(h, a, batch, smem_limit, s);
         case 64:  return hanser_launch_n<T, 64>(h, a, batch, smem_limit, s);

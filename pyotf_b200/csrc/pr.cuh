@@ -32,6 +32,7 @@ template <typename T> struct PrPlaneArgs {
     const double* kzc;          // [KR][K]
     const cplx<T>* pupilc;      // [KR][K] current pupil (compact, zero padded rows)
     const cplx<T>* tw;          // [N]
+    const cplx<T>* dtab;        // [nz][dtab_size] per-plane defocus tables (TAB variants) or nullptr
     const double* z;            // [nz]
     const T* data;              // [nz][N][N] measured stack, fftshift-ed like PSFi
     cplx<T>* partial;           // [nz * R][K][K]
@@ -40,11 +41,36 @@ template <typename T> struct PrPlaneArgs {
     int K, KR, KP, f0, nz;
 };
 
-template <typename T, int N, int M, bool TAB>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pr_plane_kernel(PrPlaneArgs<T> a) {
+// new_psf = sqrt(max(data, 0)) * exp(i angle(a))  (psqrt, phaseretrieval.py:79; :120-122), I = |a|^2.
+// angle(0) = 0, so a vanishing model amplitude gives the real value sqrt(data).
+// fp64: exact division / square root.  fp32: sqrt.approx * rsqrt.approx (2^-22 relative error, no
+// slow-path subroutine: 78 % of the fixture's pixels are zero after background subtraction and
+// 0 / x takes the IEEE division's slow path), with tiny amplitudes rescaled so that I stays normal.
+__device__ __forceinline__ cplx<double> replace_magnitude(cplx<double> a, double I, double data) {
+    const double m = sqrt(fmax(data, 0.0));
+    if (I > 0.0) return cscale(a, m / sqrt(I));
+    return mk<double>(m, 0.0);
+}
+__device__ __forceinline__ cplx<float> replace_magnitude(cplx<float> a, float I, float data) {
+    float m, r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(fmaxf(data, 0.0f)));
+    if (I < 1e-30f) {                                  // |a| < 1e-15: rescale (or a == 0)
+        a.x *= 1e20f; a.y *= 1e20f;
+        I = a.x * a.x + a.y * a.y;
+        if (!(I > 0.0f)) return mk<float>(m, 0.0f);
+    }
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(I));
+    const float s = m * r;
+    return mk<float>(a.x * s, a.y * s);
+}
+
+// NTH = 256 (two CTAs per SM) or 512 (one wide CTA per SM: short stacks, where there are fewer plane
+// quarters than SMs and latency hiding has to come from inside the CTA).
+template <typename T, int N, int M, bool TAB, int NTH>
+__global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) pr_plane_kernel(PrPlaneArgs<T> a) {
     using RP = FftPlan<N>;
     using CP = FftPlan<M>;
-    using SM = HanserSmem<N, M, T>;
+    using SM = HanserSmem<N, M, T, NTH>;
     constexpr int NT = SM::NT;
     constexpr int R = N / M;
     if (a.state->stopped) return;
@@ -53,11 +79,11 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pr_plane_kernel(P
     cplx<T>* tws = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* U = tws + N;
     cplx<T>* EX = U + (size_t)M * a.KP;
-    cplx<T>* Dq = EX;                                            // aliases EX (disjoint phases)
 
     const int tid = threadIdx.x;
     const int r = blockIdx.x % R;
     const int plane = blockIdx.x / R;
+    const cplx<T>* __restrict__ Dq = TAB ? a.dtab + (size_t)plane * dtab_size(a.f0) : nullptr;
     const int K = a.K, KP = a.KP, f0 = a.f0;
     const double z = a.z[plane];
     const cplx<T>* __restrict__ pupil = a.pupilc;
@@ -78,12 +104,11 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pr_plane_kernel(P
     const int rl = (tid >> 5) / ncw;
     const bool colactive = rl < nrl && kx < K;
 
-    if constexpr (TAB) hanser_build_dtab<T, NT>(Dq, kzc, z, f0, K, tid);
     __syncthreads();
     // ---------------- inverse: fold + columns ----------------
     {
         constexpr int Q1 = CP::R1, L1 = CP::R2;
-        if (colactive) hanser_fold_cols<TAB, true, T, N, M, false>(U, tws, Dq, nullptr, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
+        if (colactive) hanser_fold_cols<TAB, FOLD_PUPIL, T, N, M>(U, tws, Dq, nullptr, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
         if constexpr (L1 > 1) {
             __syncthreads();
             if (colactive) {
@@ -141,13 +166,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pr_plane_kernel(P
                     const T I = t[u][c2].x * t[u][c2].x + t[u][c2].y * t[u][c2].y;   // model PSFi
                     const T d = dv[c2] - I;
                     macc += d * d;                               // _calc_mse  phaseretrieval.py:401-403
-                    const T m = sqrt(fmax(dv[c2], (T)0));        // psqrt(data)  :79
-                    if (I > (T)0) {
-                        const T s = m / sqrt(I);                 // mag * exp(i angle(PSFa))  :120-122
-                        t[u][c2] = cscale(t[u][c2], s);
-                    } else {
-                        t[u][c2] = mk<T>(m, 0);                  // angle(0) = 0
-                    }
+                    t[u][c2] = replace_magnitude(t[u][c2], I, dv[c2]);   // :79, :120-122
                 }
             }
             mse_acc += (double)macc;
@@ -176,7 +195,6 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pr_plane_kernel(P
     // ---------------- forward columns: FFT_M over y' (transpose of the inverse stages) ----------------
     {
         constexpr int Q1 = CP::R1, L1 = CP::R2, JMAX = N / L1;
-        if constexpr (TAB) hanser_build_dtab<T, NT>(Dq, kzc, z, f0, K, tid);   // EX is free again
         if constexpr (L1 > 1) {
             if (colactive) {
                 for (int c1 = rl; c1 < Q1; c1 += nrl) {
@@ -192,7 +210,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) pr_plane_kernel(P
         __syncthreads();
         if (colactive) {
             const int fx = f0 + kx, ax = fx < 0 ? -fx : fx;
-            const int HP = 1 - f0;
+            const int HP = dtab_pitch(f0);
             cplx<T>* __restrict__ outp = a.partial + (size_t)blockIdx.x * K * K + kx;
             for (int bp = rl; bp < L1; bp += nrl) {
                 const int iy0 = (bp - f0) & (L1 - 1);

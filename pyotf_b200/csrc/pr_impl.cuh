@@ -7,23 +7,22 @@
 
 namespace pyotf {
 
-template <typename T> size_t pr_smem_for(int N, int M, int KP, int ntab) {
+template <typename T> size_t pr_smem_for(int N, int M, int KP) {
     switch (N) {
-        case 32:  return hanser_smem_for<T, 32>(M, KP, ntab);
-        case 64:  return hanser_smem_for<T, 64>(M, KP, ntab);
-        case 128: return hanser_smem_for<T, 128>(M, KP, ntab);
-        default:  return hanser_smem_for<T, 256>(M, KP, ntab);
+        case 32:  return hanser_smem_for<T, 32>(M, KP);
+        case 64:  return hanser_smem_for<T, 64>(M, KP);
+        case 128: return hanser_smem_for<T, 128>(M, KP);
+        default:  return hanser_smem_for<T, 256>(M, KP);
     }
 }
 
 // rows per CTA: the largest M that lets two CTAs share an SM; fewer rows (more CTAs) when the
 // stack is too short to fill the GPU otherwise.
 template <typename T> int pr_pick_rows(const pyotf_hanser* h, int nz, int smem_limit, int sm_count, int want) {
-    const int ntab = hanser_ntab<T>(h);
     const int cand[3] = {64, 32, 16};
     if (want) {
         for (int i = 0; i < 3; ++i)
-            if (cand[i] == want && want <= h->N && pr_smem_for<T>(h->N, want, h->KP, ntab) <= (size_t)smem_limit) return want;
+            if (cand[i] == want && want <= h->N && pr_smem_for<T>(h->N, want, h->KP) <= (size_t)smem_limit) return want;
         return 0;
     }
     int pick = 0;
@@ -32,49 +31,53 @@ template <typename T> int pr_pick_rows(const pyotf_hanser* h, int nz, int smem_l
             int M = cand[i];
             if (M > h->N) continue;
             size_t lim = pass == 0 ? (size_t)(smem_limit / 2 - 1024) : (size_t)smem_limit;
-            if (pr_smem_for<T>(h->N, M, h->KP, ntab) <= lim) pick = M;
+            if (pr_smem_for<T>(h->N, M, h->KP) <= lim) pick = M;
         }
     while (pick > 32 && nz * (h->N / pick) < sm_count) pick /= 2;
     return pick;
 }
 
-template <typename T, int N, int M, bool TAB>
-int pr_plane_launch_nmt(const PrPlaneArgs<T>& a, size_t smem, cudaStream_t s) {
-    auto kern = pr_plane_kernel<T, N, M, TAB>;
+template <typename T, int N, int M, bool TAB, int NTH>
+int pr_plane_launch_nmt(const PrPlaneArgs<T>& a, cudaStream_t s) {
+    const size_t smem = HanserSmem<N, M, T, NTH>::bytes(a.KP);
+    auto kern = pr_plane_kernel<T, N, M, TAB, NTH>;
     static thread_local size_t configured = 0;
     if (smem > configured) {
         PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kern<<<(unsigned)((N / M) * a.nz), 256, smem, s>>>(a);
+    kern<<<(unsigned)((N / M) * a.nz), NTH, smem, s>>>(a);
     PYOTF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 template <typename T, int N, int M>
-int pr_plane_launch_nm(const pyotf_hanser* h, const PrPlaneArgs<T>& a, cudaStream_t s) {
-    int ntab = hanser_ntab<T>(h);
-    size_t smem = HanserSmem<N, M, T>::bytes(a.KP, ntab);
-    return ntab ? pr_plane_launch_nmt<T, N, M, true>(a, smem, s) : pr_plane_launch_nmt<T, N, M, false>(a, smem, s);
+int pr_plane_launch_nm(const pyotf_hanser* h, int nth, const PrPlaneArgs<T>& a, cudaStream_t s) {
+    if (nth == 512) {
+        // the wide variant needs at least 512 / 32 = 16 warps of column work: only the 256^2 plans
+        if constexpr (N == 256 && M == 64)
+            return a.dtab ? pr_plane_launch_nmt<T, N, M, true, 512>(a, s) : pr_plane_launch_nmt<T, N, M, false, 512>(a, s);
+    }
+    return a.dtab ? pr_plane_launch_nmt<T, N, M, true, 256>(a, s) : pr_plane_launch_nmt<T, N, M, false, 256>(a, s);
 }
 
-template <typename T, int N> int pr_plane_launch_n(const pyotf_hanser* h, int M, const PrPlaneArgs<T>& a, cudaStream_t s) {
-    if (M == 64) { if constexpr (N >= 64) return pr_plane_launch_nm<T, N, 64>(h, a, s); }
-    if (M == 32) { if constexpr (N >= 32) return pr_plane_launch_nm<T, N, 32>(h, a, s); }
-    return pr_plane_launch_nm<T, N, 16>(h, a, s);
+template <typename T, int N> int pr_plane_launch_n(const pyotf_hanser* h, int M, int nth, const PrPlaneArgs<T>& a, cudaStream_t s) {
+    if (M == 64) { if constexpr (N >= 64) return pr_plane_launch_nm<T, N, 64>(h, nth, a, s); }
+    if (M == 32) { if constexpr (N >= 32) return pr_plane_launch_nm<T, N, 32>(h, nth, a, s); }
+    return pr_plane_launch_nm<T, N, 16>(h, nth, a, s);
 }
 
 template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, cudaStream_t st) {
     const pyotf_hanser* h = s->h;
     PrPlaneArgs<T> a;
-    a.kzc = h->kzc; a.pupilc = (const cplx<T>*)s->pupil[cur]; a.tw = (const cplx<T>*)h->tw; a.z = s->z;
+    a.kzc = h->kzc; a.pupilc = (const cplx<T>*)s->pupil[cur]; a.tw = (const cplx<T>*)h->tw; a.dtab = (const cplx<T>*)s->dtab; a.z = s->z;
     a.data = (const T*)s->data; a.partial = (cplx<T>*)s->partial; a.mse_part = s->mse_part; a.state = (const PrState*)s->state;
     a.K = h->K; a.KR = h->KR; a.KP = h->KP; a.f0 = h->f0; a.nz = s->nz;
     switch (h->N) {
-        case 32:  return pr_plane_launch_n<T, 32>(h, s->M, a, st);
-        case 64:  return pr_plane_launch_n<T, 64>(h, s->M, a, st);
-        case 128: return pr_plane_launch_n<T, 128>(h, s->M, a, st);
-        case 256: return pr_plane_launch_n<T, 256>(h, s->M, a, st);
+        case 32:  return pr_plane_launch_n<T, 32>(h, s->M, s->nth, a, st);
+        case 64:  return pr_plane_launch_n<T, 64>(h, s->M, s->nth, a, st);
+        case 128: return pr_plane_launch_n<T, 128>(h, s->M, s->nth, a, st);
+        case 256: return pr_plane_launch_n<T, 256>(h, s->M, s->nth, a, st);
         default: break;
     }
     set_error("pr: size must be one of 32, 64, 128, 256 on the fused path");
@@ -86,7 +89,16 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
     int smem_limit = 0, sms = 0;
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-    s->M = pr_pick_rows<T>(h, s->nz, smem_limit, sms, want_rows);
+    s->nth = 256;
+    if (want_rows == 0 && h->N == 256 && sizeof(T) == 4 &&
+        HanserSmem<256, 64, T, 512>::bytes(h->KP) <= (size_t)smem_limit) {
+        s->M = 64; s->nth = 512;      // one wide CTA per SM (16 warps): measured faster than two narrow ones
+    } else if (want_rows < 0) {
+        want_rows = -want_rows; s->nth = 512;   // tuning knob: force the wide variant (256^2, M = 64 only)
+        s->M = pr_pick_rows<T>(h, s->nz, smem_limit, sms, want_rows);
+    } else {
+        s->M = pr_pick_rows<T>(h, s->nz, smem_limit, sms, want_rows);
+    }
     PYOTF_REQUIRE(s->M != 0, "pr_create: no rows-per-CTA choice fits shared memory at this size / dtype");
     s->nparts = s->nz * (h->N / s->M);
     const size_t KK = (size_t)h->K * h->K, KKP = (size_t)h->KR * h->K, npix = (size_t)s->nz * h->N * h->N;
@@ -107,6 +119,12 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
     pr_init_pupil_kernel<T><<<(unsigned)((KKP + 255) / 256), 256, 0, st>>>(h->maskc, (int)KKP, (cplx<T>*)s->pupil[0],
                                                                           (cplx<T>*)s->pupil[1]);
     PYOTF_CUDA_OK(cudaGetLastError());
+    // the defocus tables depend on the plane positions only: built once per stack
+    if (const int ntab = hanser_ntab<T>(h)) {
+        PYOTF_CUDA_OK(cudaMalloc(&s->dtab, (size_t)s->nz * ntab * sizeof(cplx<T>)));
+        int rc = hanser_build_dtabs<T>(h, s->z, s->nz, false, (cplx<T>*)s->dtab, st);
+        if (rc) return rc;
+    }
     s->cur = 0; s->applied = 0;
     return 0;
 }
