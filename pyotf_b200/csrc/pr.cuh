@@ -293,10 +293,20 @@ struct PrFinalArgs {
     double pupil_tol, mse_tol;
 };
 
-// deterministic warp sum of v[0], v[stride], ... (n terms): same order in every CTA
+// deterministic warp sum of v[0], v[stride], ... (n terms): same order in every CTA.  The loads of a
+// chunk of 16 x 32 terms are all issued before the first add, so a sum costs one L2 round trip.
 __device__ __forceinline__ double warp_sum_fixed(const double* __restrict__ v, int n, int stride, int lane) {
     double s = 0.0;
-    for (int i = lane; i < n; i += 32) s += v[(size_t)i * stride];
+    for (int base = 0; base < n; base += 16 * 32) {
+        double t[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int i = base + lane + 32 * k;
+            t[k] = i < n ? v[(size_t)i * stride] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s += t[k];
+    }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
 }
@@ -357,10 +367,15 @@ __global__ void __launch_bounds__(256) pr_finalize_kernel(PrFinalArgs a, const T
             if (lane == 0) { const double2 v = reinterpret_cast<const double2*>(partial)[p]; sx = v.x; sy = v.y; }
         } else {
             const cplx<T>* __restrict__ pp = reinterpret_cast<const cplx<T>*>(partial) + p;
-#pragma unroll 4
-            for (int q = lane; q < a.nparts; q += PR_FIN_LANES) {
-                const cplx<T> v = pp[(size_t)q * KK];
-                sx += (double)v.x; sy += (double)v.y;
+            for (int q0 = lane; q0 < a.nparts; q0 += 16 * PR_FIN_LANES) {    // 16 loads in flight per thread
+                cplx<T> v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int q = q0 + k * PR_FIN_LANES;
+                    v[k] = q < a.nparts ? pp[(size_t)q * KK] : mk<T>(0, 0);
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { sx += (double)v[k].x; sy += (double)v[k].y; }
             }
         }
     }
