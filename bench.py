@@ -237,8 +237,120 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100):
         out["e2e"] = {"iters_per_s": iters / dt_s, "ms_total": 1e3 * dt_s, "h2d_bytes": int(data.nbytes),
                       "d2h_bytes": int(r.pupil.nbytes + 3 * 8 * iters),
                       "path": "retrieve_phase(host ndarray) -> PhaseRetrievalResult incl. host unwrap"}
+    if world > 1:
+        # replicas: every rank retrieves the full stack on its own GPU at the same time (no collective) --
+        # the batched-independent-retrievals mode SURVEY.md section 8e recommends for short stacks
+        dfull = torch.as_tensor(np.ascontiguousarray(data.astype(dt)), device="cuda")
+        st2 = eng.PRState(PR_PARAMS["wl"], PR_PARAMS["na"], PR_PARAMS["ni"], PR_PARAMS["res"], 256, zall, dfull, precision)
+        rt = []
+        for rep in range(reps + 1):
+            st2.set_pupil(None)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            st2.run(iters, 0.0, 0.0)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rep >= 1:
+                rt.append(float(t.item()))
+        out["replicas"] = {"iters_per_s": world * iters / (min(rt) * 1e-3), "us_per_iter": 1e3 * min(rt) / iters,
+                           "scaling": "weak", "note": f"{world} independent retrievals of the fixture stack, one per GPU"}
     if comm is not None:
         comm.close()
+    return out
+
+
+def _time_gpu(fn, reps, warmup=2):
+    """Best CUDA-event time (ms) of fn() over `reps` repetitions on the current stream."""
+    import torch
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(warmup):
+        fn()
+    best = None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return best
+
+
+def bench_other_configs(precision, rank, world):
+    """Device-resident throughput of BASELINE configs 3, 4 and 5 on this rank's shard (short runs; the
+    parity of each config is covered by tests/, these are the numbers DESIGN.md quotes)."""
+    import torch
+
+    from pyotf_b200 import _engine as eng
+    from pyotf_b200 import _fft, _sheppard
+    from pyotf_b200.otf import HanserPSF, SheppardPSF, _aberrated_pupils
+
+    out = {}
+    rt = torch.float32 if precision == "fp32" else torch.float64
+    es = 4 if precision == "fp32" else 8
+    # ---- config 5: PSF library, 8192 x (120 Noll phase coefs -> 256^2 x 64 PSFi), batch-sharded -------------
+    base = HanserPSF(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=256, zsize=64, precision=precision)
+    coefs = np.random.default_rng(0).standard_normal((8192, 120)) * 0.1
+    lo, hi = eng.shard_bounds(8192, rank, world)
+    B = 128                                                   # entries per launch: 2.1 GiB of fp32 PSFi
+    mine = coefs[lo:hi][:4 * B]
+    ring = [torch.empty((B, 64, 256, 256), dtype=rt, device="cuda") for _ in range(2)]
+    z = eng.to_device_f64(base.zrange)
+    pc = [eng.to_device_f64(mine[i * B:(i + 1) * B]) for i in range(len(mine) // B)]
+    state = {"i": 0}
+
+    def lib_step():
+        i = state["i"] = state["i"] + 1
+        pupils = _aberrated_pupils(base, None, pc[i % len(pc)])
+        pupils.handle(base).psf(z, pupils.tensor, want_psfa=False, want_psfi=True, psfi_out=ring[i % 2])
+
+    ms = _time_gpu(lib_step, reps=4)
+    out["library_cfg5"] = {"entries_per_s": B / (ms * 1e-3), "planes_per_s": B * 64 / (ms * 1e-3), "ms_per_launch": ms,
+                           "entries_per_launch": B, "achieved_GBps": B * 64 * 256 * 256 * es / (ms * 1e-3) / 1e9,
+                           "note": "120 Noll coefs -> aberrated pupil kernel + K1 per launch; outputs alternate over "
+                                   "2 x 2.1 GiB buffers (the 8192-entry library is 137 GB: streamed, never resident)"}
+    del ring
+    # ---- config 4: 1024^2 planes with 15 Zernike phase terms, z-sharded --------------------------------------
+    big = HanserPSF(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=1024, zsize=1024, precision=precision)
+    lo, hi = eng.shard_bounds(1024, rank, world)
+    zc = eng.to_device_f64(big.zrange[lo:hi][:64])
+    pup = _aberrated_pupils(big, None, (np.random.default_rng(0).standard_normal(15) * 0.2)[None])
+    hb = pup.handle(big)
+    outb = [torch.empty((1, 64, 1024, 1024), dtype=rt, device="cuda") for _ in range(2)]
+    state["i"] = 0
+
+    def big_step():
+        i = state["i"] = state["i"] + 1
+        hb.psf(zc, pup.tensor, want_psfa=False, want_psfi=True, psfi_out=outb[i % 2])
+
+    ms = _time_gpu(big_step, reps=4)
+    out["hanser1024_cfg4"] = {"planes_per_s": 64 / (ms * 1e-3), "ms_per_64_planes": ms,
+                              "achieved_GBps": 64 * 1024 * 1024 * es / (ms * 1e-3) / 1e9,
+                              "note": "two-pass K1b, 64-plane chunk of the 1024-plane stack per step"}
+    del outb
+    # ---- config 3: SheppardPSF 256^3 (zres=190; the 200 of BASELINE.json raises ValueError in the reference) ----
+    sh = SheppardPSF(wl=520, na=1.27, ni=1.33, res=100, zres=190, size=256, zsize=256, precision=precision)
+
+    def shep_step():
+        sh._attribute_changed()
+        return sh.PSFi_dev
+
+    ms = _time_gpu(shep_step, reps=4)
+    out["sheppard_cfg3"] = {"volumes_per_s": 1 / (ms * 1e-3), "ms_per_volume": ms,
+                            "achieved_GBps": 256 ** 3 * es / (ms * 1e-3) / 1e9,
+                            "note": "shell generator + shifted 3D inverse FFT + |.|^2 -> PSFi (replicas only across GPUs)"}
+    # ---- config 1 epilogue: OTFi from the resident PSFi --------------------------------------------------------
+    m = HanserPSF(precision=precision, **CFG1)
+    psfi = m.PSFi_dev
+    ms = _time_gpu(lambda: _fft.shifted_fft_dev(psfi, axes=None, inverse=False), reps=4)
+    out["otfi_cfg1"] = {"ms": ms, "achieved_GBps": 128 * 256 * 256 * 3 * es / (ms * 1e-3) / 1e9,
+                        "note": "shifted 3D FFT of the resident 128 x 256^2 PSFi (algorithmic bytes: real read + complex write)"}
+    torch.cuda.empty_cache()
     return out
 
 
@@ -322,9 +434,10 @@ def run_ours(args):
     # ---- e2e through the public API: host zrange in, host PSFi (numpy) out, every step ----
     model = HanserPSF(precision=precision, **CFG1)
     z_host = torch.from_numpy(zr.copy()).pin_memory()
-    for _ in range(2):
+    p = None
+    for _ in range(4):   # warm-up: lets the pinned staging pool reach its steady state (two buffers)
         model.zrange = z_host.numpy()
-        _ = model.PSFi
+        p = model.PSFi
     barrier()
     ksteps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
@@ -342,6 +455,9 @@ def run_ours(args):
     pr = None
     if not args.no_pr:
         pr = bench_pr(precision, rank, world, dist)
+    others = None
+    if not args.no_others:
+        others = bench_other_configs(precision, rank, world)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -375,6 +491,8 @@ def run_ours(args):
             # per step: hanser_dtab_kernel (per-plane defocus tables) + hanser_psf_kernel
             "gpu_launches": 2 * args.steps,
         }
+        if others is not None:
+            line["other_configs"] = others       # rank 0's shard only
         if pr is not None:
             line["phase_retrieval"] = pr
         if world == 1 and not args.no_cpu:
@@ -397,6 +515,7 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-pr", action="store_true", help="skip the phase-retrieval leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the config 3/4/5 legs")
     ap.add_argument("--min-seconds", type=float, default=1.0,
                     help="repeat the K-step measurement for at least this long (clock sampling); 0 = once")
     args = ap.parse_args()

@@ -310,15 +310,24 @@ def hanser_defocus(kz_dev, z_dev):
     return out
 
 
+def _coef_tensor(c):
+    """[B, nmodes] float64 CUDA tensor from a host array or a CUDA tensor (None stays None)."""
+    if c is None:
+        return None
+    torch = _torch()
+    if not isinstance(c, np.ndarray) and hasattr(c, "is_cuda"):
+        t = c.to(device="cuda", dtype=torch.float64)
+        return (t[None] if t.dim() == 1 else t).contiguous()
+    return to_device_f64(np.atleast_2d(np.asarray(c, dtype=np.float64)))
+
+
 def aberration_pupil(handle, n, m, mcoefs, pcoefs):
-    """Compact pupils [B, K, K] for [B, nmodes] coefficient arrays (either may be None)."""
+    """Compact pupils [B, K, K] for [B, nmodes] coefficient arrays / CUDA tensors (either may be None)."""
     torch = _torch()
     _, ct = torch_dtypes(handle.precision)
-    ref = mcoefs if mcoefs is not None else pcoefs
-    ref = np.atleast_2d(np.asarray(ref, dtype=np.float64))
-    B, nmodes = ref.shape
-    mc = to_device_f64(np.atleast_2d(mcoefs)) if mcoefs is not None else None
-    pc = to_device_f64(np.atleast_2d(pcoefs)) if pcoefs is not None else None
+    mc, pc = _coef_tensor(mcoefs), _coef_tensor(pcoefs)
+    ref = mc if mc is not None else pc
+    B, nmodes = int(ref.shape[0]), int(ref.shape[1])
     nd, md = to_device_i32(n), to_device_i32(m)
     out = torch.empty((B, handle.KR, handle.K), dtype=ct, device="cuda")
     _lib.check(_lib.load().pyotf_b200_hanser_aberration_pupil(handle._h, ptr(nd), ptr(md), nmodes, ptr(mc), ptr(pc), B,

@@ -17,46 +17,50 @@ namespace pyotf {
 template <typename T> struct BigArgs {
     const double* kzc;        // [KR][K]
     const T* ampc;            // [KR][K] of the current polarisation component
-    const cplx<T>* pupilc;    // [B][..] compact pupils or nullptr
-    long long pupil_stride;
-    const double* z;          // [nz] (already offset to the chunk)
-    cplx<T>* W;               // [B][nzc][K][N]
-    cplx<T>* psfa;            // [B][nvec][nz][N][N] offset to (component, chunk) or nullptr
-    T* psfi;                  // [B][nz][N][N] offset to the chunk or nullptr
-    long long psfa_bstride, psfi_bstride;   // elements between batch entries
+    const cplx<T>* pupilc;    // [KR][K] compact pupil of this batch entry or nullptr
+    const cplx<T>* tw;        // [N] e^{+2 pi i k / N} (the handle's table)
+    const double* z;          // [nzc] (already offset to the chunk)
+    cplx<T>* W;               // [nzc][K][N]
+    cplx<T>* psfa;            // [nzc][N][N] of this (entry, component, chunk) or nullptr
+    T* psfi;                  // [nzc][N][N] of this (entry, chunk) or nullptr
     int N, K, f0, nzc, accumulate;
     double scale;
 };
 
-// generic line FFT: line index -> functor-defined loads / stores.  LINES are processed TI per CTA.
-// LD(line, l) -> cplx<T> (l = input index along the transformed axis, natural order)
-// ST(line, l, value)      (l = output index, natural order)
-template <int DIR, typename T, int L, int TI, bool POW2, bool LINE_MAJOR, class LD, class ST>
-__global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nlines_total, LD ld, ST st) {
+// generic line FFT: the functor F maps a line index to a small descriptor once per line
+// (F::Line info(line)), then loads / stores elements of that line:
+//   F::load(const Line&, l) -> cplx<T>   (l = input index along the transformed axis, natural order)
+//   F::store(const Line&, o, value)      (o = output index, natural order)
+// TI lines per CTA.  LINE_MAJOR: consecutive threads walk along one line (the axis is contiguous in
+// memory); otherwise consecutive threads take consecutive lines (the lines are contiguous).
+template <int DIR, typename T, int L, int TI, bool POW2, bool LINE_MAJOR, class F>
+__global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nlines_total, F f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ typename F::Line sline[TI];
     const int Lr = POW2 ? L : Lrt;
     const int pitch = Lr + 1;
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* tile = tw + Lr;
     cplx<T>* tile2 = tile + (size_t)TI * pitch;
-    for (int k = threadIdx.x; k < Lr; k += blockDim.x) {
-        double s, c;
-        sincospi(2.0 * (double)k / (double)Lr, &s, &c);
-        tw[k] = mk<T>((T)c, (T)s);
-    }
     const long long line0 = (long long)blockIdx.x * TI;
     const int nlines = (int)min((long long)TI, nlines_total - line0);
-    // LINE_MAJOR: consecutive threads walk along one line (the axis is contiguous in memory);
-    // otherwise consecutive threads take consecutive lines (the lines are contiguous).
+    if (threadIdx.x < nlines) sline[threadIdx.x] = f.info(line0 + threadIdx.x);
+    for (int k = threadIdx.x; k < Lr; k += blockDim.x) tw[k] = f.twiddle(k);   // e^{+2 pi i k / L}, precomputed
+    __syncthreads();
     if (LINE_MAJOR) {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int t = w / Lr, l = w - t * Lr;
-            tile[(size_t)t * pitch + l] = ld(line0 + t, l);
+            tile[(size_t)t * pitch + l] = f.load(sline[t], l);
+        }
+    } else if (nlines == TI) {                       // full tile: compile-time divisor
+        for (int w = threadIdx.x; w < TI * Lr; w += blockDim.x) {
+            int l = w / TI, t = w - l * TI;
+            tile[(size_t)t * pitch + l] = f.load(sline[t], l);
         }
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int l = w / nlines, t = w - l * nlines;
-            tile[(size_t)t * pitch + l] = ld(line0 + t, l);
+            tile[(size_t)t * pitch + l] = f.load(sline[t], l);
         }
     }
     __syncthreads();
@@ -87,73 +91,84 @@ __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nline
             int t = w / Lr, o = w - t * Lr;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            st(line0 + t, o, res[(size_t)t * pitch + pos]);
+            f.store(sline[t], o, res[(size_t)t * pitch + pos]);
+        }
+    } else if (nlines == TI) {
+        for (int w = threadIdx.x; w < TI * Lr; w += blockDim.x) {
+            int o = w / TI, t = w - o * TI;
+            int pos = o;
+            if constexpr (POW2) pos = digit_reversed_pos<L>(o);
+            f.store(sline[t], o, res[(size_t)t * pitch + pos]);
         }
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int o = w / nlines, t = w - o * nlines;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            st(line0 + t, o, res[(size_t)t * pitch + pos]);
+            f.store(sline[t], o, res[(size_t)t * pitch + pos]);
         }
     }
 }
 
-// ---- pass A: line = (b, plane, iy), axis = kx ---------------------------------------------
-template <typename T> struct BigRowLoad {
+// ---- pass A: line = (plane, iy), axis = kx --------------------------------------------------
+template <typename T> struct BigRow {
+    struct Line { int iy; double z; cplx<T>* w; };
     BigArgs<T> a;
-    __device__ __forceinline__ cplx<T> operator()(long long line, int l) const {
-        const int iy = (int)(line % a.K);
-        const long long bp = line / a.K;
-        const int plane = (int)(bp % a.nzc), b = (int)(bp / a.nzc);
+    __device__ __forceinline__ Line info(long long line) const {
+        Line d;
+        d.iy = (int)(line % a.K);
+        d.z = a.z[(int)(line / a.K)];
+        d.w = a.W + (size_t)line * a.N;
+        return d;
+    }
+    __device__ __forceinline__ cplx<T> load(const Line& d, int l) const {
         const int f = l < (a.N + 1) / 2 ? l : l - a.N;
         const int ix = f - a.f0;
         if (ix < 0 || ix >= a.K) return mk<T>(0, 0);
-        const int off = iy * a.K + ix;
+        const int off = d.iy * a.K + ix;
         const T am = a.ampc[off];
         if (am == (T)0 && !a.pupilc) return mk<T>(0, 0);
-        cplx<T> d;
-        cis_cycles(a.kzc[off] * a.z[plane], d);                  // _calc_defocus   otf.py:357-360
-        cplx<T> v = cscale(d, am);
-        if (a.pupilc) v = cmul(v, a.pupilc[(size_t)b * a.pupil_stride + off]);
+        cplx<T> v;
+        cis_cycles(a.kzc[off] * d.z, v);                         // _calc_defocus   otf.py:357-360
+        v = cscale(v, am);
+        if (a.pupilc) v = cmul(v, a.pupilc[off]);
         return v;
     }
+    __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v) const { d.w[o] = v; }   // x stays unshifted
+    __device__ __forceinline__ cplx<T> twiddle(int k) const { return a.tw[k]; }
 };
-template <typename T> struct BigRowStore {
+// ---- pass B: line = (plane, x), axis = ky ---------------------------------------------------
+template <typename T> struct BigCol {
+    struct Line { const cplx<T>* w; cplx<T>* psfa; T* psfi; };
     BigArgs<T> a;
-    __device__ __forceinline__ void operator()(long long line, int o, cplx<T> v) const {
-        a.W[(size_t)line * a.N + o] = v;                           // x stays unshifted here
+    __device__ __forceinline__ Line info(long long line) const {
+        const int x = (int)(line % a.N), plane = (int)(line / a.N);
+        const int xs = (x + a.N / 2) % a.N;                       // fftshift   otf.py:426
+        const size_t base = (size_t)plane * a.N * a.N + xs;
+        Line d;
+        d.w = a.W + (size_t)plane * a.K * a.N + x;
+        d.psfa = a.psfa ? a.psfa + base : nullptr;
+        d.psfi = a.psfi ? a.psfi + base : nullptr;
+        return d;
     }
-};
-// ---- pass B: line = (b, plane, x), axis = ky ----------------------------------------------
-template <typename T> struct BigColLoad {
-    BigArgs<T> a;
-    __device__ __forceinline__ cplx<T> operator()(long long line, int l) const {
-        const int x = (int)(line % a.N);
-        const long long bp = line / a.N;
+    __device__ __forceinline__ cplx<T> load(const Line& d, int l) const {
         const int f = l < (a.N + 1) / 2 ? l : l - a.N;
         const int iy = f - a.f0;
         if (iy < 0 || iy >= a.K) return mk<T>(0, 0);
-        return a.W[((size_t)bp * a.K + iy) * a.N + x];
+        return d.w[(size_t)iy * a.N];
     }
-};
-template <typename T> struct BigColStore {
-    BigArgs<T> a;
-    __device__ __forceinline__ void operator()(long long line, int o, cplx<T> v) const {
-        const int x = (int)(line % a.N);
-        const long long bp = line / a.N;
-        const int plane = (int)(bp % a.nzc), b = (int)(bp / a.nzc);
-        const int xs = (x + a.N / 2) % a.N, ys = (o + a.N / 2) % a.N;     // fftshift   otf.py:426
+    __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v) const {
+        int ys = o + a.N / 2; if (ys >= a.N) ys -= a.N;            // fftshift
         const T sc = (T)a.scale;
         v = cscale(v, sc);
-        const size_t pix = ((size_t)plane * a.N + ys) * a.N + xs;
-        if (a.psfa) a.psfa[(size_t)b * a.psfa_bstride + pix] = v;
-        if (a.psfi) {
-            T* p = a.psfi + (size_t)b * a.psfi_bstride + pix;
+        const size_t off = (size_t)ys * a.N;
+        if (d.psfa) d.psfa[off] = v;
+        if (d.psfi) {
             const T I = v.x * v.x + v.y * v.y;
-            if (a.accumulate) *p += I; else *p = I;                        // otf.py:204-207
+            if (a.accumulate) d.psfi[off] += I; else d.psfi[off] = I;      // otf.py:204-207
         }
     }
+    __device__ __forceinline__ cplx<T> twiddle(int k) const { return a.tw[k]; }
 };
 
 }  // namespace pyotf

@@ -40,6 +40,16 @@ def main():
         st = eng.PRState(520, 0.85, 1.0, 130, 256, zall, torch.as_tensor(data.astype(dt), device="cuda"), precision)
         mse, _, _ = st.run(6, 0.0, 0.0)
         print("pr ok", mse[-1])
+    if "big" in what:
+        from pyotf_b200.otf import HanserPSF, _aberrated_pupils
+
+        big = HanserPSF(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=1024, zsize=1024, precision=precision)
+        pup = _aberrated_pupils(big, None, (np.random.default_rng(0).standard_normal(15) * 0.2)[None])
+        zc = eng.to_device_f64(big.zrange[:26])
+        for _ in range(2):
+            _, psfi = pup.handle(big).psf(zc, pup.tensor)
+        torch.cuda.synchronize()
+        print("big ok", float(psfi.sum()))
     if "otf" in what:
         from pyotf_b200.otf import HanserPSF
 
