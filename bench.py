@@ -476,7 +476,7 @@ def run_ours(args):
             "dtype": "f32" if precision == "fp32" else "f64", "data": "synthetic",
             "config": {"workload": "hanser256: HanserPSF(wl=520,na=0.85,ni=1.0,res=130,zres=300,size=256,"
                                    "zsize=128) -> PSFi (BASELINE config 1)",
-                       "step": "one K1 pass over the 128-plane stack per GPU (defocus-table kernel + fused plane kernel)",
+                       "step": "one fused K1 launch over the 128-plane stack per GPU",
                        "l2": "outputs rotate over 8 x 32 MiB buffers (256 MiB > 126 MB L2)",
                        "timing": f"best of {reps} repetitions of exactly {args.steps} steps, CUDA events on the "
                                  f"launch stream, max over ranks",
@@ -488,8 +488,8 @@ def run_ours(args):
             "e2e": {"value": nz * world / e2e_s, "unit": "planes/s", "h2d_bytes_per_step": int(zr.nbytes),
                     "d2h_bytes_per_step": int(nz * N * N * esize), "ms_per_step": 1e3 * e2e_s,
                     "path": "HanserPSF.zrange = host array; HanserPSF.PSFi -> numpy (pinned D2H)"},
-            # per step: hanser_dtab_kernel (per-plane defocus tables) + hanser_psf_kernel
-            "gpu_launches": 2 * args.steps,
+            # per step: one hanser_psf_kernel launch (4-CTA clusters build the defocus tables through DSMEM)
+            "gpu_launches": args.steps,
         }
         if others is not None:
             line["other_configs"] = others       # rank 0's shard only

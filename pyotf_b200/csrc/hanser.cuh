@@ -14,6 +14,8 @@
 //            the store index).
 // No intermediate ever leaves the SM; the only HBM traffic is the PSFi/PSFa store.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "fft_regs.cuh"
 
 namespace pyotf {
@@ -150,6 +152,7 @@ template <int N, int M, typename T, int NTHREADS = 256> struct HanserSmem {
     static constexpr int NG = NT / RP::G;                     // row groups per CTA
     static constexpr int PITCH = RP::R2 + 1;                  // exchange pitch (elements)
     static constexpr int EXSZ = ((RP::R1 * PITCH + 7) / 8) * 8 + (RP::G == 8 ? 8 : 0);
+    static constexpr int EXTOT = NG * EXSZ;                   // elements of the exchange region (also stages the defocus table)
     // twiddles + column/row work area U + the row-exchange buffers
     __host__ __device__ static size_t bytes(int KP) {
         return sizeof(cplx<T>) * ((size_t)N + (size_t)M * KP + (size_t)NG * EXSZ);
@@ -194,6 +197,38 @@ __global__ void __launch_bounds__(256) hanser_dtab_kernel(const double* __restri
 // cyclic offset m0 is repaid after the butterfly as the phase w_Q1^{m0 c} (shift theorem),
 // merged into the stage twiddle.  Each group of Q1 rows is branch-free (clamped address,
 // zero weight when out of range) so its global loads issue back to back.
+// The same table built cooperatively by the R CTAs of one plane (a thread-block cluster): each CTA
+// evaluates 1/R of the octant entries and writes them into the shared memory of every CTA of the
+// cluster through distributed shared memory.  Used when one stack is generated per launch (no batch
+// to amortise a separate table kernel over): no extra launch, 1/R of the sincos work per CTA.
+template <typename T, int NT, int R>
+__device__ __forceinline__ void hanser_build_dtab_cluster(cplx<T>* Dq, const double* __restrict__ kzc,
+                                                          const T* __restrict__ amp, double z, int f0, int K,
+                                                          int tid, int rank) {
+    const int H = -f0, HP = dtab_pitch(f0), W = H + 2, ntot = (H / 2 + 1) * W;
+    cplx<T>* dst[R];
+    if constexpr (R > 1) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+        for (int c = 0; c < R; ++c) dst[c] = cluster.map_shared_rank(Dq, c);
+    } else {
+        dst[0] = Dq;                                   // R == 1: plain per-CTA build, no cluster needed
+    }
+    for (int e = rank * NT + tid; e < ntot; e += R * NT) {
+        const int p = e / W, t = e - p * W;
+        int i, j;
+        if (t <= p) { i = p; j = t; } else { i = H - p; j = t - p - 1; }
+        if (t > p && i == p) continue;                 // the middle row of an even H is its own partner
+        const unsigned o = (unsigned)((H + i) * K + (H + j));
+        cplx<T> d;
+        cis_cycles(kzc[o] * z, d);
+        if (amp) d = cscale(d, amp[o]);
+#pragma unroll
+        for (int c = 0; c < R; ++c) { dst[c][i * HP + j] = d; dst[c][j * HP + i] = d; }
+    }
+}
+
 // what multiplies the defocus factor in the fold
 enum FoldMode {
     FOLD_TAB_ONLY = 0,    // nothing: the table already holds amp * D      (ideal pupil, scalar model)
@@ -281,8 +316,17 @@ __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const 
 // when the support box is symmetric each CTA evaluates it once per octant entry (i >= j >= 0)
 // into a shared-memory quadrant table instead of once per pupil pixel (6x fewer sincos for the
 // 256^2 configs).
-template <typename T, int N, int M, bool TAB>
+// TABM: 0 = defocus evaluated on the fly, 1 = per-plane tables precomputed in global memory and staged,
+// 2 = table built by the plane's R-CTA cluster through distributed shared memory, 3 = every CTA builds
+// its own copy (one stack per launch: cheaper than a separate table launch).
+// SYM: ideal pupil of the scalar model.  pupil * amp * D then depends on (|ky|, |kx|) only, so the PSF is
+// even in y and in x: the fold runs over the columns kx >= 0 only (the row pass reads column |kx|) and
+// only the rows y <= N/2 are transformed, each stored to y and to N - y.  Halves both halves of the work
+// for the reference's default model (HanserPSF with no aberration), bit-identical otherwise.
+template <typename T, int N, int M, int TABM, bool SYM>
 __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
+    constexpr bool TAB = TABM != 0;
+    static_assert(!SYM || TAB, "the symmetric path needs the (symmetric-box) table");
     using RP = FftPlan<N>;
     using CP = FftPlan<M>;
     using SM = HanserSmem<N, M, T>;
@@ -297,7 +341,9 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
     const int r = blockIdx.x % R;
     const int plane = blockIdx.x / R;
     const int bidx = blockIdx.y;
-    const cplx<T>* __restrict__ Dq = TAB ? a.dtab + (size_t)plane * dtab_size(a.f0) : nullptr;
+    // TAB: this plane's defocus table is staged into the (still idle) exchange region: the fold's
+    // lookups are shared-memory hits instead of L2 round trips
+    cplx<T>* Dq = EX;
     const int K = a.K, KP = a.KP, f0 = a.f0, KK = a.KR * K;
     const double z = a.z[plane];
     const cplx<T>* __restrict__ pupil = a.pupilc ? a.pupilc + (size_t)bidx * a.pupil_stride : nullptr;
@@ -314,16 +360,35 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
     for (int c = 0; c < RP::R1; ++c) twr[c] = cscale(a.tw[(g * c) & (N - 1)], scale);
 
     // column-parallel mapping for fold + column FFT: a warp owns 32 consecutive kx
-    const int ncw = (K + 31) >> 5;                 // warps needed to cover the K columns
+    const int kx0 = SYM ? -f0 : 0;                 // SYM: only the columns with fx >= 0
+    const int ncols = K - kx0;
+    const int ncw = (ncols + 31) >> 5;             // warps needed to cover the columns
     const int nrl = (NT / 32) / ncw;               // row lanes (>= 1 because K <= 256)
-    const int kx = ((tid >> 5) % ncw) * 32 + (tid & 31);
+    const int kx = kx0 + ((tid >> 5) % ncw) * 32 + (tid & 31);
     const int rl = (tid >> 5) / ncw;
     const bool colactive = rl < nrl && kx < K;
 
     const size_t plane_elems = (size_t)N * N;
 
     for (int v = 0; v < a.nvec; ++v) {
-        __syncthreads();                                         // previous component's rows are done with EX
+        if constexpr (TABM == 2) {
+            // every CTA of the cluster is done with its exchange region before anyone writes into it
+            cooperative_groups::this_cluster().sync();
+            const bool amp_in = a.amp_in_tab != 0;
+            hanser_build_dtab_cluster<T, NT, R>(Dq, kzc, amp_in ? a.ampc : nullptr, z, f0, K, tid, r);
+            cooperative_groups::this_cluster().sync();
+        } else {
+            __syncthreads();                                     // previous component's rows are done with EX
+            if constexpr (TABM == 3) {
+                hanser_build_dtab_cluster<T, NT, 1>(Dq, kzc, a.amp_in_tab ? a.ampc : nullptr, z, f0, K, tid, 0);
+                __syncthreads();
+            }
+            if constexpr (TABM == 1) {
+                const cplx<T>* __restrict__ src = a.dtab + (size_t)plane * dtab_size(a.f0);
+                for (int i = tid; i < dtab_size(a.f0); i += NT) Dq[i] = src[i];
+                __syncthreads();
+            }
+        }
         // scalar model + ideal pupil: the (radially symmetric) apodisation rides in the defocus table
         const bool tab_only = TAB && a.amp_in_tab;
         const T* __restrict__ amp = a.ampc + (size_t)v * KK;
@@ -360,15 +425,31 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
             T* const psfi_plane = a.psfi ? a.psfi + ((size_t)bidx * a.nz + plane) * plane_elems : nullptr;
             cplx<T>* const psfa_plane =
                 a.psfa ? a.psfa + (((size_t)bidx * a.nvec + v) * a.nz + plane) * plane_elems : nullptr;
-            for (int l = grp; l < M; l += NG) {
+            // SYM: the rows with y = R*y' + r <= N/2 only, i.e. y' < M/2 (plus y' = M/2 when r == 0)
+            constexpr int HC = CL1 > 1 ? CL1 / 2 : 1;
+            const int nrows = SYM ? M / 2 + (r == 0 ? 1 : 0) : M;
+            for (int i = grp; i < nrows; i += NG) {
+                int l = i;
+                if constexpr (SYM) {
+                    if constexpr (CL1 > 1) l = i < M / 2 ? (i / HC) * CL1 + (i % HC) : CL1 / 2;
+                    else l = i;                                      // y' = l, rows 0 .. M/2
+                }
                 const int yp = (l / CL1) + CQ1 * (l % CL1);
-                const int ys = (R * yp + r + N / 2) & (N - 1);
+                const int y = R * yp + r;
+                const int ys = (y + N / 2) & (N - 1);
+                const int ym = (N - y) & (N - 1);                    // mirror row (SYM)
+                const bool mirror = SYM && ym != y;
+                const int ysm = (ym + N / 2) & (N - 1);
                 const cplx<T>* Ul = U + (size_t)l * KP;
                 cplx<T> x[R1];
 #pragma unroll
                 for (int q = 0; q < R1; ++q) {
                     // k = L1*q + g ; positive half k < N/2, else frequency k - N
                     if (L1 * q < N / 2) x[q] = (ipos + L1 * q < K) ? Ul[ipos + L1 * q] : mk<T>(0, 0);
+                    else if constexpr (SYM) {                        // column |k - N| = N - k
+                        const int af = N - L1 * q - g;
+                        x[q] = (af <= -f0) ? Ul[af - f0] : mk<T>(0, 0);
+                    }
                     else x[q] = (ineg + L1 * q >= 0) ? Ul[ineg + L1 * q] : mk<T>(0, 0);
                 }
                 fft_radix<1, R1>(x);
@@ -389,6 +470,12 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
 #pragma unroll
                         for (int c2 = 0; c2 < L1; ++c2)
                             row[R1 * c2 < N / 2 ? R1 * c2 + N / 2 : R1 * c2 - N / 2] = t[c2];
+                        if (mirror) {
+                            row = psfa_plane + (size_t)ysm * N + c1;
+#pragma unroll
+                            for (int c2 = 0; c2 < L1; ++c2)
+                                row[R1 * c2 < N / 2 ? R1 * c2 + N / 2 : R1 * c2 - N / 2] = t[c2];
+                        }
                     }
                     if (psfi_plane) {
                         T* row = psfi_plane + (size_t)ys * N + c1;
@@ -397,6 +484,13 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
                             for (int c2 = 0; c2 < L1; ++c2)
                                 row[R1 * c2 < N / 2 ? R1 * c2 + N / 2 : R1 * c2 - N / 2] =
                                     t[c2].x * t[c2].x + t[c2].y * t[c2].y;
+                            if (mirror) {
+                                row = psfi_plane + (size_t)ysm * N + c1;
+#pragma unroll
+                                for (int c2 = 0; c2 < L1; ++c2)
+                                    row[R1 * c2 < N / 2 ? R1 * c2 + N / 2 : R1 * c2 - N / 2] =
+                                        t[c2].x * t[c2].x + t[c2].y * t[c2].y;
+                            }
                         } else {
 #pragma unroll
                             for (int c2 = 0; c2 < L1; ++c2)

@@ -1,6 +1,7 @@
 // Per-dtype host launchers for K1 (instantiated in hanser_f32.cu / hanser_f64.cu).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "hanser.cuh"
@@ -33,10 +34,19 @@ int hanser_pack(const pyotf_hanser* h, const void* src, int batch, void* dst, cu
     return 0;
 }
 
-// entries of one per-plane defocus table when the support box is symmetric about DC, else 0
-template <typename T> int hanser_ntab(const pyotf_hanser* h) {
+// entries of one per-plane defocus table when the support box is symmetric about DC and the table
+// fits the kernels' exchange region (where it is staged), else 0 (defocus evaluated on the fly)
+template <typename T> int hanser_ntab(const pyotf_hanser* h, int nthreads = 256) {
     if (h->K != 2 * (-h->f0) + 1) return 0;
-    return dtab_size(h->f0);
+    int cap = 0;
+    switch (h->N) {       // EXTOT does not depend on M
+        case 32:  cap = nthreads == 512 ? HanserSmem<32, 16, T, 512>::EXTOT : HanserSmem<32, 16, T>::EXTOT; break;
+        case 64:  cap = nthreads == 512 ? HanserSmem<64, 16, T, 512>::EXTOT : HanserSmem<64, 16, T>::EXTOT; break;
+        case 128: cap = nthreads == 512 ? HanserSmem<128, 16, T, 512>::EXTOT : HanserSmem<128, 16, T>::EXTOT; break;
+        case 256: cap = nthreads == 512 ? HanserSmem<256, 16, T, 512>::EXTOT : HanserSmem<256, 16, T>::EXTOT; break;
+        default: return 0;
+    }
+    return dtab_size(h->f0) <= cap ? dtab_size(h->f0) : 0;
 }
 
 // (re)build the per-plane defocus tables of a stack into `dst` ([nz][ntab])
@@ -50,26 +60,43 @@ int hanser_build_dtabs(const pyotf_hanser* h, const double* z, int nz, bool with
     return 0;
 }
 
-template <typename T, int N, int M, bool TAB>
+template <typename T, int N, int M, int TABM, bool SYM = false>
 int hanser_launch_nmt(const HanserArgs<T>& a, int batch, size_t smem, cudaStream_t s) {
     using SM = HanserSmem<N, M, T>;
-    auto kern = hanser_psf_kernel<T, N, M, TAB>;
+    auto kern = hanser_psf_kernel<T, N, M, TABM, SYM>;
     static thread_local size_t configured = 0;
     if (smem > configured) {
         PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     dim3 grid((unsigned)((N / M) * a.nz), (unsigned)batch);
-    kern<<<grid, SM::NT, smem, s>>>(a);
+    if constexpr (TABM == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(SM::NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = N / M; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PYOTF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
+    } else {
+        kern<<<grid, SM::NT, smem, s>>>(a);
+    }
     PYOTF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 template <typename T, int N, int M>
-int hanser_launch_nm(const pyotf_hanser* h, const HanserArgs<T>& a, int batch, cudaStream_t s) {
+int hanser_launch_nm(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int batch, cudaStream_t s) {
     size_t smem = HanserSmem<N, M, T>::bytes(a.KP);
-    return a.dtab ? hanser_launch_nmt<T, N, M, true>(a, batch, smem, s)
-                  : hanser_launch_nmt<T, N, M, false>(a, batch, smem, s);
+    if (tabm == 2) {
+        if constexpr (N / M <= 8) return hanser_launch_nmt<T, N, M, 2>(a, batch, smem, s);
+    }
+    // ideal pupil of the scalar model: the even-symmetric variant (half the columns, half the rows)
+    static const bool no_sym = getenv("PYOTF_B200_K1_NOSYM") != nullptr;
+    const bool sym = a.amp_in_tab && !no_sym;
+    if (tabm == 3) return sym ? hanser_launch_nmt<T, N, M, 3, true>(a, batch, smem, s) : hanser_launch_nmt<T, N, M, 3>(a, batch, smem, s);
+    if (tabm == 1) return sym ? hanser_launch_nmt<T, N, M, 1, true>(a, batch, smem, s) : hanser_launch_nmt<T, N, M, 1>(a, batch, smem, s);
+    return hanser_launch_nmt<T, N, M, 0>(a, batch, smem, s);
 }
 
 template <typename T, int N> size_t hanser_smem_for(int M, int KP) {
@@ -78,11 +105,15 @@ template <typename T, int N> size_t hanser_smem_for(int M, int KP) {
     return HanserSmem<N, (N >= 64 ? 64 : 16), T>::bytes(KP);
 }
 
+// picks rows-per-CTA M; *m_out receives it when only the choice is wanted (launch = false)
 template <typename T, int N>
-int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int batch, int smem_limit, cudaStream_t s) {
+int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int batch, int smem_limit, cudaStream_t s,
+                    int* m_out = nullptr) {
     // largest rows-per-CTA M whose working set allows two CTAs per SM, else the largest that fits
     int pick = 0;
     const int cand[3] = {64, 32, 16};
+    static const int forced = [] { const char* e = getenv("PYOTF_B200_K1_ROWS"); return e ? atoi(e) : 0; }();   // tuning knob
+    if (forced && forced <= N && hanser_smem_for<T, N>(forced, a.KP) <= (size_t)smem_limit) pick = forced;
     for (int pass = 0; pass < 2 && !pick; ++pass)
         for (int i = 0; i < 3 && !pick; ++i) {
             int M = cand[i];
@@ -92,9 +123,10 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int batch, in
             if (need <= lim) pick = M;
         }
     PYOTF_REQUIRE(pick != 0, "hanser_psf: pupil support too large for the fused on-chip path at this size/dtype");
-    if (pick == 64) { if constexpr (N >= 64) return hanser_launch_nm<T, N, 64>(h, a, batch, s); }
-    if (pick == 32) { if constexpr (N >= 32) return hanser_launch_nm<T, N, 32>(h, a, batch, s); }
-    return hanser_launch_nm<T, N, 16>(h, a, batch, s);
+    if (m_out) { *m_out = pick; return 0; }
+    if (pick == 64) { if constexpr (N >= 64) return hanser_launch_nm<T, N, 64>(h, a, tabm, batch, s); }
+    if (pick == 32) { if constexpr (N >= 32) return hanser_launch_nm<T, N, 32>(h, a, tabm, batch, s); }
+    return hanser_launch_nm<T, N, 16>(h, a, tabm, batch, s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -180,27 +212,45 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     a.dtab = nullptr; a.amp_in_tab = 0;
     const int ntab = hanser_ntab<T>(h);
-    if (ntab && (h->N == 32 || h->N == 64 || h->N == 128 || h->N == 256)) {
-        // per-plane defocus tables (one small launch per stack); the handle owns the scratch.
-        // NOTE: a handle must not be used from two streams at once (the scratch is shared).
-        pyotf_hanser* hm = const_cast<pyotf_hanser*>(h);
-        const size_t need = (size_t)nz * ntab * sizeof(cplx<T>);
-        if (need > hm->dtab_cap) {
-            PYOTF_CUDA_OK(cudaStreamSynchronize(s));
-            cudaFree(hm->dtab); hm->dtab = nullptr; hm->dtab_cap = 0;
-            PYOTF_CUDA_OK(cudaMalloc(&hm->dtab, need));
-            hm->dtab_cap = need;
-        }
+    const bool fused = h->N == 32 || h->N == 64 || h->N == 128 || h->N == 256;
+    int tabm = 0;
+    if (ntab && fused) {
         a.amp_in_tab = (!pupilc && h->nvec == 1) ? 1 : 0;
-        int rc = hanser_build_dtabs<T>(h, z, nz, a.amp_in_tab != 0, (cplx<T>*)hm->dtab, s);
+        int M = 0, rc = 0;
+        switch (h->N) {
+            case 32:  rc = hanser_launch_n<T, 32>(h, a, 0, batch, smem_limit, s, &M); break;
+            case 64:  rc = hanser_launch_n<T, 64>(h, a, 0, batch, smem_limit, s, &M); break;
+            case 128: rc = hanser_launch_n<T, 128>(h, a, 0, batch, smem_limit, s, &M); break;
+            default:  rc = hanser_launch_n<T, 256>(h, a, 0, batch, smem_limit, s, &M); break;
+        }
         if (rc) return rc;
-        a.dtab = (const cplx<T>*)hm->dtab;
+        static const int k1_tab = [] { const char* e = getenv("PYOTF_B200_K1_TABLE"); return e ? atoi(e) : 0; }();
+        if (batch == 1 && k1_tab == 2 && h->N / M <= 8) {
+            tabm = 2;       // experiment: the plane's CTA cluster builds the table through DSMEM (measured slower)
+        } else if (batch == 1 && k1_tab != 1) {
+            tabm = 3;       // one stack: every CTA builds its own table (no separate launch)
+        } else {
+            // a batch shares the per-plane tables: one small launch per stack; the handle owns the scratch.
+            // NOTE: a handle must not be used from two streams at once (the scratch is shared).
+            tabm = 1;
+            pyotf_hanser* hm = const_cast<pyotf_hanser*>(h);
+            const size_t need = (size_t)nz * ntab * sizeof(cplx<T>);
+            if (need > hm->dtab_cap) {
+                PYOTF_CUDA_OK(cudaStreamSynchronize(s));
+                cudaFree(hm->dtab); hm->dtab = nullptr; hm->dtab_cap = 0;
+                PYOTF_CUDA_OK(cudaMalloc(&hm->dtab, need));
+                hm->dtab_cap = need;
+            }
+            rc = hanser_build_dtabs<T>(h, z, nz, a.amp_in_tab != 0, (cplx<T>*)hm->dtab, s);
+            if (rc) return rc;
+            a.dtab = (const cplx<T>*)hm->dtab;
+        }
     }
     switch (h->N) {
-        case 32:  return hanser_launch_n<T, 32>(h, a, batch, smem_limit, s);
-        case 64:  return hanser_launch_n<T, 64>(h, a, batch, smem_limit, s);
-        case 128: return hanser_launch_n<T, 128>(h, a, batch, smem_limit, s);
-        case 256: return hanser_launch_n<T, 256>(h, a, batch, smem_limit, s);
+        case 32:  return hanser_launch_n<T, 32>(h, a, tabm, batch, smem_limit, s);
+        case 64:  return hanser_launch_n<T, 64>(h, a, tabm, batch, smem_limit, s);
+        case 128: return hanser_launch_n<T, 128>(h, a, tabm, batch, smem_limit, s);
+        case 256: return hanser_launch_n<T, 256>(h, a, tabm, batch, smem_limit, s);
         default: break;
     }
     return hanser_launch_big<T>(h, z, nz, pupilc, batch, pupil_stride, psfa, psfi, smem_limit, s);

@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
     const int tid = threadIdx.x;
     const int r = blockIdx.x % R;
     const int plane = blockIdx.x / R;
-    const cplx<T>* __restrict__ Dq = TAB ? a.dtab + (size_t)plane * dtab_size(a.f0) : nullptr;
+    cplx<T>* Dq = EX;                                            // staged defocus table (aliases EX, disjoint phases)
+    const cplx<T>* __restrict__ dsrc = TAB ? a.dtab + (size_t)plane * dtab_size(a.f0) : nullptr;
+    if constexpr (TAB) for (int i = tid; i < dtab_size(a.f0); i += NT) Dq[i] = dsrc[i];
     const int K = a.K, KP = a.KP, f0 = a.f0;
     const double z = a.z[plane];
     const cplx<T>* __restrict__ pupil = a.pupilc;
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
     // ---------------- forward columns: FFT_M over y' (transpose of the inverse stages) ----------------
     {
         constexpr int Q1 = CP::R1, L1 = CP::R2, JMAX = N / L1;
+        if constexpr (TAB) for (int i = tid; i < dtab_size(a.f0); i += NT) Dq[i] = dsrc[i];   // EX is free again
         if constexpr (L1 > 1) {
             if (colactive) {
                 for (int c1 = rl; c1 < Q1; c1 += nrl) {
