@@ -39,6 +39,9 @@ struct pyotf_hanser {
     void* ampc = nullptr;           // [nvec*K*K] dtype
     unsigned char* maskc = nullptr; // [K*K]
     void* tw = nullptr;             // [N] complex dtype
+    double* octkz = nullptr;        // octant lists (symmetric box only): kz, amp of component 0, packed (i, j)
+    void* octamp = nullptr;
+    int* octij = nullptr;
     void* dtab = nullptr;           // [planes][dtab_size] per-plane defocus tables (scratch, grown on demand)
     size_t dtab_cap = 0;            // capacity of dtab in bytes
 };

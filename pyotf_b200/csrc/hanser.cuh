@@ -139,6 +139,9 @@ template <typename T> struct HanserArgs {
     const cplx<T>* tw;        // [N] e^{+2 pi i k/N}
     const cplx<T>* dtab;      // [nz][dtab_size] per-plane defocus tables (TAB variants) or nullptr
     int amp_in_tab;           // the tables already hold amp * D (ideal pupil, scalar model)
+    const double* octkz;      // octant lists for the in-kernel table builders (symmetric box) or nullptr
+    const T* octamp;
+    const int* octij;
     const double* z;          // [nz]
     T* psfi;                  // [B][nz][N][N] or nullptr
     cplx<T>* psfa;            // [B][nvec][nz][N][N] or nullptr
@@ -197,15 +200,31 @@ __global__ void __launch_bounds__(256) hanser_dtab_kernel(const double* __restri
 // cyclic offset m0 is repaid after the butterfly as the phase w_Q1^{m0 c} (shift theorem),
 // merged into the stage twiddle.  Each group of Q1 rows is branch-free (clamped address,
 // zero weight when out of range) so its global loads issue back to back.
-// The same table built cooperatively by the R CTAs of one plane (a thread-block cluster): each CTA
-// evaluates 1/R of the octant entries and writes them into the shared memory of every CTA of the
-// cluster through distributed shared memory.  Used when one stack is generated per launch (no batch
-// to amortise a separate table kernel over): no extra launch, 1/R of the sincos work per CTA.
+// Octant lists for the in-kernel table builders: entry e (row-pair order, see hanser_dtab_kernel) ->
+// kz, amp of component 0 and the packed (i << 16 | j) position.  Built once per handle so that the
+// builders read three coalesced streams instead of decoding indices and gathering from the K x K tables.
+template <typename T>
+__global__ void hanser_oct_kernel(const double* __restrict__ kzc, const T* __restrict__ amp, int f0, int K,
+                                  double* __restrict__ octkz, T* __restrict__ octamp, int* __restrict__ octij) {
+    const int H = -f0, W = H + 2, ntot = (H / 2 + 1) * W;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ntot) return;
+    const int p = e / W, t = e - p * W;
+    int i, j;
+    if (t <= p) { i = p; j = t; } else { i = H - p; j = t - p - 1; }
+    if (t > p && i == p) { octij[e] = -1; octkz[e] = 0.0; octamp[e] = (T)0; return; }   // unused slot (even H)
+    const unsigned o = (unsigned)((H + i) * K + (H + j));
+    octkz[e] = kzc[o]; octamp[e] = amp[o]; octij[e] = (i << 16) | j;
+}
+
+// The defocus table of one plane built inside the PSF kernel.  R == 1: every CTA builds its own copy.
+// R > 1: the R CTAs of the plane (a thread-block cluster) each evaluate 1/R of the entries and write
+// them into the shared memory of every CTA of the cluster through distributed shared memory.
 template <typename T, int NT, int R>
-__device__ __forceinline__ void hanser_build_dtab_cluster(cplx<T>* Dq, const double* __restrict__ kzc,
-                                                          const T* __restrict__ amp, double z, int f0, int K,
-                                                          int tid, int rank) {
-    const int H = -f0, HP = dtab_pitch(f0), W = H + 2, ntot = (H / 2 + 1) * W;
+__device__ __forceinline__ void hanser_build_dtab_cluster(cplx<T>* Dq, const double* __restrict__ octkz,
+                                                          const T* __restrict__ octamp, const int* __restrict__ octij,
+                                                          bool with_amp, double z, int f0, int tid, int rank) {
+    const int H = -f0, HP = dtab_pitch(f0), ntot = (H / 2 + 1) * (H + 2);
     cplx<T>* dst[R];
     if constexpr (R > 1) {
         namespace cg = cooperative_groups;
@@ -213,19 +232,32 @@ __device__ __forceinline__ void hanser_build_dtab_cluster(cplx<T>* Dq, const dou
 #pragma unroll
         for (int c = 0; c < R; ++c) dst[c] = cluster.map_shared_rank(Dq, c);
     } else {
-        dst[0] = Dq;                                   // R == 1: plain per-CTA build, no cluster needed
+        dst[0] = Dq;
     }
-    for (int e = rank * NT + tid; e < ntot; e += R * NT) {
-        const int p = e / W, t = e - p * W;
-        int i, j;
-        if (t <= p) { i = p; j = t; } else { i = H - p; j = t - p - 1; }
-        if (t > p && i == p) continue;                 // the middle row of an even H is its own partner
-        const unsigned o = (unsigned)((H + i) * K + (H + j));
-        cplx<T> d;
-        cis_cycles(kzc[o] * z, d);
-        if (amp) d = cscale(d, amp[o]);
+    constexpr int UNR = 4;
+    for (int e0 = rank * NT + tid; e0 < ntot; e0 += UNR * R * NT) {
+        double kz[UNR];
+        T am[UNR];
+        int ij[UNR];
 #pragma unroll
-        for (int c = 0; c < R; ++c) { dst[c][i * HP + j] = d; dst[c][j * HP + i] = d; }
+        for (int u = 0; u < UNR; ++u) {                 // all loads of the batch before the first sincos
+            const int e = e0 + u * R * NT;
+            const bool ok = e < ntot;
+            ij[u] = ok ? octij[e] : -1;
+            kz[u] = ok ? octkz[e] : 0.0;
+            am[u] = (ok && with_amp) ? octamp[e] : (T)1;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            if (ij[u] >= 0) {
+                const int i = ij[u] >> 16, j = ij[u] & 0xffff;
+                cplx<T> d;
+                cis_cycles(kz[u] * z, d);                // _calc_defocus   otf.py:357-360
+                d = cscale(d, am[u]);
+#pragma unroll
+                for (int c = 0; c < R; ++c) { dst[c][i * HP + j] = d; dst[c][j * HP + i] = d; }
+            }
+        }
     }
 }
 
@@ -375,12 +407,12 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
             // every CTA of the cluster is done with its exchange region before anyone writes into it
             cooperative_groups::this_cluster().sync();
             const bool amp_in = a.amp_in_tab != 0;
-            hanser_build_dtab_cluster<T, NT, R>(Dq, kzc, amp_in ? a.ampc : nullptr, z, f0, K, tid, r);
+            hanser_build_dtab_cluster<T, NT, R>(Dq, a.octkz, a.octamp, a.octij, amp_in, z, f0, tid, r);
             cooperative_groups::this_cluster().sync();
         } else {
             __syncthreads();                                     // previous component's rows are done with EX
             if constexpr (TABM == 3) {
-                hanser_build_dtab_cluster<T, NT, 1>(Dq, kzc, a.amp_in_tab ? a.ampc : nullptr, z, f0, K, tid, 0);
+                hanser_build_dtab_cluster<T, NT, 1>(Dq, a.octkz, a.octamp, a.octij, a.amp_in_tab != 0, z, f0, tid, 0);
                 __syncthreads();
             }
             if constexpr (TABM == 1) {

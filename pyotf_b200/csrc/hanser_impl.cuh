@@ -22,6 +22,15 @@ template <typename T> int hanser_build_tables(pyotf_hanser* h, cudaStream_t s) {
     PYOTF_CUDA_OK(cudaGetLastError());
     twiddle_kernel<T><<<(h->N + 255) / 256, 256, 0, s>>>(h->N, (cplx<T>*)h->tw);
     PYOTF_CUDA_OK(cudaGetLastError());
+    if (h->K == 2 * (-h->f0) + 1 && h->K < h->N) {      // symmetric support box: octant lists for the table builders
+        const int H = -h->f0, ntot = (H / 2 + 1) * (H + 2);
+        PYOTF_CUDA_OK(cudaMalloc(&h->octkz, sizeof(double) * ntot));
+        PYOTF_CUDA_OK(cudaMalloc(&h->octamp, sizeof(T) * ntot));
+        PYOTF_CUDA_OK(cudaMalloc(&h->octij, sizeof(int) * ntot));
+        hanser_oct_kernel<T><<<(ntot + 255) / 256, 256, 0, s>>>(h->kzc, (const T*)h->ampc, h->f0, h->K, h->octkz,
+                                                              (T*)h->octamp, h->octij);
+        PYOTF_CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -211,7 +220,8 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
     int smem_limit = 0;
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     a.dtab = nullptr; a.amp_in_tab = 0;
-    const int ntab = hanser_ntab<T>(h);
+    a.octkz = h->octkz; a.octamp = (const T*)h->octamp; a.octij = h->octij;
+    const int ntab = h->octkz ? hanser_ntab<T>(h) : 0;
     const bool fused = h->N == 32 || h->N == 64 || h->N == 128 || h->N == 256;
     int tabm = 0;
     if (ntab && fused) {
