@@ -125,6 +125,13 @@ typedef struct pyotf_sheppard_params {
  * PSFi = pyotf_b200_abs2_sum0(PSFa)                                         (otf.py:204-207). */
 int pyotf_b200_sheppard_otfa(const pyotf_sheppard_params* params, void* otfa_out_dev, unsigned char* valid_out_dev,
                              void* stream);
+/* K3 fused -- OTFa, PSFa (otf.py:589-592) and PSFi (otf.py:204-207) of one model in one call; any output
+ * may be NULL (scratch is stream-ordered).  The generator records which kz planes / (kz, ky) rows hold
+ * shell voxels and the first two passes of the 3D inverse FFT skip the all-zero lines (at BASELINE
+ * config 3 only 87 of 256 planes and 17 % of the rows are occupied).
+ *   otfa_out_dev, psfa_out_dev [nvec][zsize][size][size] complex, shifted; psfi_out_dev [zsize][size][size] */
+int pyotf_b200_sheppard_psf(const pyotf_sheppard_params* params, void* otfa_out_dev, void* psfa_out_dev,
+                            void* psfi_out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Phase retrieval  (pyotf/phaseretrieval.py:32-149, the loop :95-135, _calc_mse :401-403)

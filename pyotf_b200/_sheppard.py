@@ -28,13 +28,34 @@ def otfa(model):
     return out
 
 
+def _fused(model, want_psfa, want_psfi):
+    """One pyotf_b200_sheppard_psf call; fills the model's device cache with everything it produced."""
+    torch = _engine._torch()
+    rt, ct = _engine.torch_dtypes(model.precision)
+    shape = (_nvec(model), model.zsize, model.size, model.size)
+    dev = model.__dict__.setdefault("_device", {})
+    otf = torch.empty(shape, dtype=ct, device="cuda")
+    psfa_t = torch.empty(shape, dtype=ct, device="cuda") if want_psfa else None
+    psfi_t = torch.empty(shape[1:], dtype=rt, device="cuda") if want_psfi else None
+    p = _params(model)
+    _lib.check(_lib.load().pyotf_b200_sheppard_psf(C.byref(p), _engine.ptr(otf), _engine.ptr(psfa_t), _engine.ptr(psfi_t),
+                                                   _engine.stream_ptr()))
+    if not model._has_result("OTFa"):
+        dev["OTFa"] = otf
+    return psfa_t, psfi_t
+
+
 def psfa(model):
     """SheppardPSF.PSFa = easy_ifft(OTFa, axes=(1, 2, 3)) (otf.py:589-592)."""
-    return _fft.shifted_fft_dev(model._device_result("OTFa"), axes=(1, 2, 3), inverse=True)
+    if model._has_result("OTFa"):      # an OTFa was assigned / cached: transform exactly that array
+        return _fft.shifted_fft_dev(model._device_result("OTFa"), axes=(1, 2, 3), inverse=True)
+    return _fused(model, True, False)[0]
 
 
 def psfi(model):
-    return _fft.abs2_sum0(model._device_result("PSFa"))
+    if model._has_result("OTFa"):
+        return _fft.abs2_sum0(model._device_result("PSFa"))
+    return _fused(model, False, True)[1]
 
 
 def gen_kr(model):

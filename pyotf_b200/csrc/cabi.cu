@@ -31,6 +31,43 @@ static int aberration_launch(const pyotf_hanser* h, const int* n, const int* m, 
 }
 
 
+static int sheppard_params(const pyotf_sheppard_params* q, SheppardParams* out) {
+    PYOTF_REQUIRE(q->wl > 0 && q->na > 0 && q->ni > 0 && q->res > 0 && q->zres > 0, "sheppard: wl, na, ni, res, zres must be positive");
+    PYOTF_REQUIRE(q->size > 0 && q->zsize > 0 && q->zsize <= 65535 && q->size <= 65535, "sheppard: bad size");
+    PYOTF_REQUIRE(q->vec_corr >= 0 && q->vec_corr <= 4 && q->condition >= 0 && q->condition <= 2, "sheppard: bad enum");
+    PYOTF_REQUIRE(q->dtype == PYOTF_F32 || q->dtype == PYOTF_F64, "sheppard: bad dtype");
+    SheppardParams p;
+    p.N = q->size; p.NZ = q->zsize; p.vec_mode = q->vec_corr; p.condition = q->condition; p.dual = q->dual ? 1 : 0;
+    p.nvec = q->vec_corr == PYOTF_VEC_NONE ? 1 : (q->vec_corr == PYOTF_VEC_TOTAL ? 6 : 2);
+    p.kstep = 1.0 / ((double)q->size * q->res);          // numpy.fft.fftfreq: val = 1.0 / (n * d)
+    p.kzstep = 1.0 / ((double)q->zsize * q->zres);
+    // dk = k[1] - k[0] (otf.py:508); a length-1 axis has no k[1]: the reference raises IndexError there
+    PYOTF_REQUIRE(q->size > 1 && q->zsize > 1, "sheppard: size and zsize must be > 1");
+    p.dk = (q->size == 2 ? -1.0 : 1.0) * p.kstep;          // fftfreq(2) = [0, -1] * val
+    p.dkz = (q->zsize == 2 ? -1.0 : 1.0) * p.kzstep;
+    p.same_dk = p.dk == p.dkz;
+    p.kmag = q->ni / q->wl;
+    const double nawl = q->na / q->wl;
+    const double arg = p.kmag * p.kmag - nawl * nawl;      // otf.py:512
+    PYOTF_REQUIRE(arg >= 0, "sheppard: na > ni");
+    p.kz_min = sqrt(arg);
+    // |kr - kmag| < dkr and dkr <= max(|dk|, |dkz|) (a weighted norm over the plain norm): bounds on kr^2, widened
+    const double dmax = fmax(fabs(p.dk), fabs(p.dkz)) * (1.0 + 1e-9);
+    const double lo = fmax(0.0, p.kmag - dmax), hi = p.kmag + dmax;
+    p.r2_lo = lo * lo * (1.0 - 1e-12); p.r2_hi = hi * hi * (1.0 + 1e-12);
+    if (p.dk < 0 || p.dkz < 0) { p.r2_lo = -1.0; p.r2_hi = 1e300; }   // degenerate 2-sample axes: no prefilter
+    *out = p;
+    return 0;
+}
+
+template <typename T>
+static void sheppard_generate(const SheppardParams& p, void* otfa, unsigned char* valid, unsigned char* rowflag,
+                              unsigned char* planeflag, cudaStream_t s) {
+    dim3 grid((unsigned)((p.N + 255) / 256), (unsigned)p.N, (unsigned)p.NZ);
+    sheppard_otf_kernel<T><<<grid, 256, 0, s>>>(p, (cplx<T>*)otfa, valid, rowflag, planeflag);
+}
+
+
 extern "C" {
 
 int pyotf_b200_abi_version(void) { return PYOTF_B200_ABI_VERSION; }
@@ -186,31 +223,58 @@ int pyotf_b200_hanser_aberration_pupil(const pyotf_hanser_t* h, const int* n, co
 
 int pyotf_b200_sheppard_otfa(const pyotf_sheppard_params* q, void* otfa, unsigned char* valid, void* stream) {
     PYOTF_REQUIRE(q && (otfa || valid), "sheppard_otfa: null argument");
-    PYOTF_REQUIRE(q->wl > 0 && q->na > 0 && q->ni > 0 && q->res > 0 && q->zres > 0, "sheppard_otfa: wl, na, ni, res, zres must be positive");
-    PYOTF_REQUIRE(q->size > 0 && q->zsize > 0 && q->zsize <= 65535 && q->size <= 65535, "sheppard_otfa: bad size");
-    PYOTF_REQUIRE(q->vec_corr >= 0 && q->vec_corr <= 4 && q->condition >= 0 && q->condition <= 2, "sheppard_otfa: bad enum");
-    PYOTF_REQUIRE(q->dtype == PYOTF_F32 || q->dtype == PYOTF_F64, "sheppard_otfa: bad dtype");
     SheppardParams p;
-    p.N = q->size; p.NZ = q->zsize; p.vec_mode = q->vec_corr; p.condition = q->condition; p.dual = q->dual ? 1 : 0;
-    p.nvec = q->vec_corr == PYOTF_VEC_NONE ? 1 : (q->vec_corr == PYOTF_VEC_TOTAL ? 6 : 2);
-    p.kstep = 1.0 / ((double)q->size * q->res);          // numpy.fft.fftfreq: val = 1.0 / (n * d)
-    p.kzstep = 1.0 / ((double)q->zsize * q->zres);
-    // dk = k[1] - k[0] (otf.py:508); a length-1 axis has no k[1]: the reference raises IndexError there
-    PYOTF_REQUIRE(q->size > 1 && q->zsize > 1, "sheppard_otfa: size and zsize must be > 1");
-    p.dk = (q->size == 2 ? -1.0 : 1.0) * p.kstep;          // fftfreq(2) = [0, -1] * val
-    p.dkz = (q->zsize == 2 ? -1.0 : 1.0) * p.kzstep;
-    p.same_dk = p.dk == p.dkz;
-    p.kmag = q->ni / q->wl;
-    const double nawl = q->na / q->wl;
-    const double arg = p.kmag * p.kmag - nawl * nawl;      // otf.py:512
-    PYOTF_REQUIRE(arg >= 0, "sheppard_otfa: na > ni");
-    p.kz_min = sqrt(arg);
-    dim3 grid((unsigned)((q->size + 255) / 256), (unsigned)q->size, (unsigned)q->zsize);
+    int rc = sheppard_params(q, &p);
+    if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    if (q->dtype == PYOTF_F32) sheppard_otf_kernel<float><<<grid, 256, 0, s>>>(p, (cplx<float>*)otfa, valid);
-    else sheppard_otf_kernel<double><<<grid, 256, 0, s>>>(p, (cplx<double>*)otfa, valid);
+    if (q->dtype == PYOTF_F32) sheppard_generate<float>(p, otfa, valid, nullptr, nullptr, s);
+    else sheppard_generate<double>(p, otfa, valid, nullptr, nullptr, s);
     PYOTF_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int pyotf_b200_sheppard_psf(const pyotf_sheppard_params* q, void* otfa_out, void* psfa_out, void* psfi_out, void* stream) {
+    PYOTF_REQUIRE(q && (otfa_out || psfa_out || psfi_out), "sheppard_psf: no output requested");
+    SheppardParams p;
+    int rc = sheppard_params(q, &p);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t es = q->dtype == PYOTF_F32 ? 4 : 8;
+    const size_t nvox = (size_t)p.NZ * p.N * p.N, nlines = (size_t)p.nvec * p.NZ * p.N;
+    void *otfa = otfa_out, *psfa = psfa_out;
+    unsigned char* flags = nullptr;         // rowflag [NZ*N] | planeflag [NZ] | f_x [nlines] | f_y [nlines]
+    const bool want_fft = psfa_out || psfi_out;
+    keep_scratch_pool();
+    if (!otfa) PYOTF_CUDA_OK(cudaMallocAsync(&otfa, nvox * p.nvec * 2 * es, s));
+    if (want_fft) {
+        PYOTF_CUDA_OK(cudaMallocAsync(&flags, (size_t)p.NZ * p.N + p.NZ + 2 * nlines, s));
+        PYOTF_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)p.NZ * p.N + p.NZ, s));
+        if (!psfa) PYOTF_CUDA_OK(cudaMallocAsync(&psfa, nvox * p.nvec * 2 * es, s));
+    }
+    unsigned char* rowflag = flags, *planeflag = flags ? flags + (size_t)p.NZ * p.N : nullptr;
+    if (q->dtype == PYOTF_F32) sheppard_generate<float>(p, otfa, nullptr, rowflag, planeflag, s);
+    else sheppard_generate<double>(p, otfa, nullptr, rowflag, planeflag, s);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    if (want_fft) {
+        unsigned char* f_x = planeflag + p.NZ, *f_y = f_x + nlines;
+        sheppard_flags_kernel<<<(unsigned)((nlines + 255) / 256), 256, 0, s>>>(p.nvec, p.NZ, p.N, rowflag, planeflag, f_x, f_y);
+        PYOTF_CUDA_OK(cudaGetLastError());
+        // PSFa = easy_ifft(OTFa, axes=(1, 2, 3))  (otf.py:589-592); passes run x, y, z
+        const long long shape[4] = {p.nvec, p.NZ, p.N, p.N};
+        const int axes[3] = {1, 2, 3};
+        // the flags are exact only when every pass's lines coincide with the rows / planes they were built for,
+        // i.e. for the contiguous x pass and the y pass; the z pass sees dense lines
+        const unsigned char* pass_flags[3] = {f_x, f_y, nullptr};
+        rc = q->dtype == PYOTF_F32 ? fftn_run<float>(otfa, psfa, 4, shape, axes, 3, 1, 0, 1, 1, s, pass_flags)
+                                   : fftn_run<double>(otfa, psfa, 4, shape, axes, 3, 1, 0, 1, 1, s, pass_flags);
+        if (!rc && psfi_out)
+            rc = q->dtype == PYOTF_F32 ? abs2_sum0_run<float>(psfa, p.nvec, (long long)nvox, psfi_out, s)
+                                       : abs2_sum0_run<double>(psfa, p.nvec, (long long)nvox, psfi_out, s);
+        cudaFreeAsync(flags, s);
+        if (!psfa_out) cudaFreeAsync(psfa, s);
+    }
+    if (!otfa_out) cudaFreeAsync(otfa, s);
+    return rc;
 }
 
 int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev, int nz, long long nz_total,

@@ -27,6 +27,20 @@ void set_error(const std::string& msg);
         }                                                                                        \
     } while (0)
 
+// Stream-ordered scratch (cudaMallocAsync) comes from the device's default pool; keep freed blocks cached
+// instead of returning them to the driver at every synchronisation (the default release threshold is 0).
+inline void keep_scratch_pool() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+}
+
 constexpr int PYOTF_PAD_ROWS = 64;   // >= the largest rows-per-CTA M of K1
 inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
@@ -86,6 +100,6 @@ template <typename T>
 int hanser_pack(const pyotf_hanser* h, const void* src, int batch, void* dst, cudaStream_t s);
 template <typename T>
 int fftn_run(const void* in, void* out, int ndim, const long long* shape, const int* axes, int naxes, int inverse,
-             int real_in, int shift_in, int shift_out, cudaStream_t s);
+             int real_in, int shift_in, int shift_out, cudaStream_t s, const unsigned char* const* pass_flags = nullptr);
 template <typename T> int abs2_sum0_run(const void* a, int nvec, long long n, void* out, cudaStream_t s);
 }  // namespace pyotf

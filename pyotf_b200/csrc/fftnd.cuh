@@ -20,6 +20,9 @@ struct AxisPass {
     int in_shift;          // x_in[i] = src[(i + in_shift) % L]
     int out_shift;         // dst[(o + out_shift) % L] = X[o]
     double scale;          // applied to outputs (1/L for inverse)
+    const void* tw;        // [L] e^{+2 pi i k / L} in the transform's dtype (device; cached per length)
+    const unsigned char* line_flags;   // optional: one byte per line (outer * n_inner + inner); 0 = the line is
+                                       // entirely zero on input, so (in place) it is left untouched
 };
 
 // radix sequence for power-of-two L (product == L): up to three stages of radix <= 16
@@ -95,10 +98,9 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
     cplx<T>* tile = tw + Lr;                                    // [TI][pitch]
     cplx<T>* tile2 = tile + (size_t)TI * pitch;                 // DFT output (non-pow2 only)
 
-    for (int k = threadIdx.x; k < Lr; k += blockDim.x) {
-        double s, c;
-        sincospi(2.0 * (double)k / (double)Lr, &s, &c);
-        tw[k] = mk<T>((T)c, (T)s);
+    {
+        const cplx<T>* __restrict__ twg = reinterpret_cast<const cplx<T>*>(p.tw);
+        for (int k = threadIdx.x; k < Lr; k += blockDim.x) tw[k] = twg[k];
     }
     // tile -> (outer, inner0)
     const long long tiles_per_outer = (p.n_inner + TI - 1) / TI;
@@ -117,6 +119,25 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
     }
     const size_t base = contiguous ? (size_t)outer * Lr : (size_t)outer * Lr * p.n_inner + inner0;
     const size_t stride_t = contiguous ? (size_t)Lr : 1, stride_l = contiguous ? 1 : (size_t)p.n_inner;
+    if (p.line_flags) {
+        // lines known to be all-zero on input transform to zero: skip the tile (zero-fill when out of place)
+        const size_t line0 = contiguous ? (size_t)outer : (size_t)outer * p.n_inner + inner0;
+        bool any = false;
+        for (int t = 0; t < nlines; ++t) any |= p.line_flags[line0 + t] != 0;     // CTA-uniform
+        if (!any) {
+            if ((const void*)src != (const void*)dst) {
+                if (contiguous) {
+                    for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) dst[base + w] = mk<T>(0, 0);
+                } else {
+                    for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
+                        int l = w / nlines, t = w - l * nlines;
+                        dst[base + t + l * stride_l] = mk<T>(0, 0);
+                    }
+                }
+            }
+            return;
+        }
+    }
 
     // ---- load (coalesced along the contiguous direction), input shift folded in ----
     if (contiguous) {

@@ -1,5 +1,6 @@
 #include "fftnd_impl.cuh"
 namespace pyotf {
-template int fftn_run<double>(const void*, void*, int, const long long*, const int*, int, int, int, int, int, cudaStream_t);
+template int fftn_run<double>(const void*, void*, int, const long long*, const int*, int, int, int, int, int, cudaStream_t,
+                             const unsigned char* const*);
 template int abs2_sum0_run<double>(const void*, int, long long, void*, cudaStream_t);
 }  // namespace pyotf

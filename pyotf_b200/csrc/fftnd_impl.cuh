@@ -1,5 +1,8 @@
 // Host launchers for the axis-pass FFT (instantiated per dtype in fftnd_f32.cu / fftnd_f64.cu).
 #pragma once
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 #include "fftnd.cuh"
 
@@ -46,10 +49,40 @@ int fft_axis_launch(const AxisPass& p, const void* src, void* dst, int smem_limi
     }
 }
 
-// out = [shift](fftn / ifftn)([shift] in) over `axes` of a C-contiguous array
+template <typename T> __global__ void fft_twiddle_kernel(int L, cplx<T>* __restrict__ tw) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L) return;
+    double sn, cs;
+    sincospi(2.0 * (double)k / (double)L, &sn, &cs);
+    tw[k] = mk<T>((T)cs, (T)sn);
+}
+
+// e^{+2 pi i k / L} for k < L, computed in fp64 once per (device, length, dtype) and kept for the process
+template <typename T> int fft_twiddles(int L, const void** out, cudaStream_t s) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, void*> cache;
+    int dev = 0;
+    PYOTF_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({dev, L});
+    if (it == cache.end()) {
+        void* p = nullptr;
+        PYOTF_CUDA_OK(cudaMalloc(&p, sizeof(cplx<T>) * (size_t)L));
+        fft_twiddle_kernel<T><<<(L + 255) / 256, 256, 0, s>>>(L, (cplx<T>*)p);
+        PYOTF_CUDA_OK(cudaGetLastError());
+        PYOTF_CUDA_OK(cudaStreamSynchronize(s));      // other streams may use the table right away
+        it = cache.emplace(std::make_pair(dev, L), p).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// out = [shift](fftn / ifftn)([shift] in) over `axes` of a C-contiguous array.
+// pass_flags: optional, one pointer per pass in execution order (the LAST listed axis runs first): per-line
+// "has data" bytes, see AxisPass::line_flags.
 template <typename T>
 int fftn_run(const void* in, void* out, int ndim, const long long* shape, const int* axes, int naxes, int inverse,
-             int real_in, int shift_in, int shift_out, cudaStream_t s) {
+             int real_in, int shift_in, int shift_out, cudaStream_t s, const unsigned char* const* pass_flags) {
     int dev = 0, smem_limit = 0;
     PYOTF_CUDA_OK(cudaGetDevice(&dev));
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -66,6 +99,11 @@ int fftn_run(const void* in, void* out, int ndim, const long long* shape, const 
         p.in_shift = shift_in ? (inverse ? rest : half) : 0;
         p.out_shift = shift_out ? (inverse ? rest : half) : 0;
         p.scale = inverse ? 1.0 / (double)p.L : 1.0;
+        p.line_flags = pass_flags ? pass_flags[naxes - 1 - k] : nullptr;
+        {
+            int rc = fft_twiddles<T>(p.L, &p.tw, s);
+            if (rc) return rc;
+        }
         const void* src = first ? in : out;
         int rc;
         if (first && real_in) rc = inverse ? fft_axis_launch<1, T, T>(p, src, out, smem_limit, s)

@@ -188,6 +188,7 @@ int hanser_launch_big(const pyotf_hanser* h, const double* z, int nz, const void
     const size_t wplane = (size_t)K * N * sizeof(cplx<T>);
     int nzc = (int)std::max<size_t>(1, std::min<size_t>((size_t)nz, ((size_t)48 << 20) / wplane));
     cplx<T>* W = nullptr;
+    keep_scratch_pool();
     PYOTF_CUDA_OK(cudaMallocAsync(&W, wplane * nzc, s));
     int rc = 0;
     for (int b = 0; b < batch && !rc; ++b)

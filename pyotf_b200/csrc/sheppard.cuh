@@ -16,6 +16,7 @@ struct SheppardParams {
     double kstep, kzstep;     // fftfreq steps 1/(N res), 1/(NZ zres)
     double dk, dkz;           // k[1] - k[0], kz[1] - kz[0]
     double kmag, kz_min;
+    double r2_lo, r2_hi;      // conservative bounds on kr^2 for a voxel to be on the shell (prefilter)
 };
 
 __device__ __forceinline__ double fftfreq_at(int i, int n, double step) {
@@ -24,17 +25,32 @@ __device__ __forceinline__ double fftfreq_at(int i, int n, double step) {
     return __dmul_rn((double)f, step);
 }
 
+// rowflag [NZ][N] / planeflag [NZ] (optional, zero-initialised, indexed in the SHIFTED layout of the output):
+// set to 1 when the row / plane holds a shell voxel; the 3D inverse FFT skips lines that are entirely zero.
 template <typename T>
 __global__ void __launch_bounds__(256) sheppard_otf_kernel(SheppardParams p, cplx<T>* __restrict__ otf,
-                                                           unsigned char* __restrict__ valid_out) {
+                                                           unsigned char* __restrict__ valid_out,
+                                                           unsigned char* __restrict__ rowflag,
+                                                           unsigned char* __restrict__ planeflag) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y, zi = blockIdx.z;
     if (x >= p.N) return;
     const double kz = fftfreq_at(zi, p.NZ, p.kzstep);
     const double ky = fftfreq_at(y, p.N, p.kstep);
     const double kx = fftfreq_at(x, p.N, p.kstep);
+    const size_t plane = (size_t)p.N * p.N, vol = plane * p.NZ;
+    // fftshift: index i moves to (i + n//2) mod n
+    const int xs = (x + p.N / 2) % p.N, ys = (y + p.N / 2) % p.N, zs = (zi + p.NZ / 2) % p.NZ;
+    const size_t o = (size_t)zs * plane + (size_t)ys * p.N + xs;
     // numpy.linalg.norm(axis=0): sqrt(add.reduce(x * x)) in array order (kz, ky, kx)
-    const double kr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(kz, kz), __dmul_rn(ky, ky)), __dmul_rn(kx, kx)));
+    const double kr2 = __dadd_rn(__dadd_rn(__dmul_rn(kz, kz), __dmul_rn(ky, ky)), __dmul_rn(kx, kx));
+    // prefilter: |kr - kmag| < dkr <= max(dk, dkz) bounds kr^2; 99.7 % of the voxels stop here
+    if (kr2 < p.r2_lo || kr2 > p.r2_hi) {
+        if (valid_out) valid_out[(size_t)zi * plane + (size_t)y * p.N + x] = 0;
+        if (otf) for (int v = 0; v < p.nvec; ++v) otf[(size_t)v * vol + o] = mk<T>(0, 0);
+        return;
+    }
+    const double kr = sqrt(kr2);
     double dkr;
     if (p.same_dk) dkr = p.dk;
     else if (zi == 0 && y == 0 && x == 0) dkr = 0.0;
@@ -44,11 +60,8 @@ __global__ void __launch_bounds__(256) sheppard_otf_kernel(SheppardParams p, cpl
     }
     const double kzz = p.dual ? fabs(kz) : kz;
     const bool valid = (fabs(__dsub_rn(kr, p.kmag)) < dkr) && (kzz > __dadd_rn(p.kz_min, dkr));
-    const size_t plane = (size_t)p.N * p.N, vol = plane * p.NZ;
     if (valid_out) valid_out[(size_t)zi * plane + (size_t)y * p.N + x] = valid ? 1 : 0;
-    // fftshift: index i moves to (i + n//2) mod n
-    const int xs = (x + p.N / 2) % p.N, ys = (y + p.N / 2) % p.N, zs = (zi + p.NZ / 2) % p.NZ;
-    const size_t o = (size_t)zs * plane + (size_t)ys * p.N + xs;
+    if (valid && rowflag) { rowflag[(size_t)zs * p.N + ys] = 1; planeflag[zs] = 1; }
     if (!otf) return;
     if (!valid) {
         for (int v = 0; v < p.nvec; ++v) otf[(size_t)v * vol + o] = mk<T>(0, 0);
@@ -74,6 +87,19 @@ __global__ void __launch_bounds__(256) sheppard_otf_kernel(SheppardParams p, cpl
         otf[(size_t)(v++) * vol + o] = mk<T>((T)((1 - m * m / (1 + s)) * a), 0);
         otf[(size_t)(v++) * vol + o] = mk<T>((T)((-m * n / (1 + s)) * a), 0);
     }
+}
+
+// per-line flags of the first two passes of the 3D inverse FFT of OTFa [nvec][NZ][N][N]:
+// pass over x: line (v, z, y) <- rowflag[z][y];  pass over y: line (v, z, x) <- planeflag[z]
+static __global__ void sheppard_flags_kernel(int nvec, int NZ, int N, const unsigned char* __restrict__ rowflag,
+                                             const unsigned char* __restrict__ planeflag,
+                                             unsigned char* __restrict__ f_x, unsigned char* __restrict__ f_y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = nvec * NZ * N;
+    if (i >= n) return;
+    const int zy = i % (NZ * N);
+    f_x[i] = rowflag[zy];
+    f_y[i] = planeflag[zy / N];
 }
 
 }  // namespace pyotf
