@@ -151,6 +151,9 @@ int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev,
 int pyotf_b200_pr_destroy(pyotf_pr_t* s);
 /* K, rows, f0 of the compact pupil layout; rows per CTA; partial pupils per iteration */
 int pyotf_b200_pr_info(const pyotf_pr_t* s, int* K, int* rows, int* f0, int* rows_per_cta, int* nparts);
+/* Inspection hook for the parity tests: device pointers of the intermediates of the last iteration
+ * (four-pass path: W [nz][K][N] and P [nz][N][N] complex; both paths: partial pupils [nparts][K][K]). */
+int pyotf_b200_pr_debug_buffers(const pyotf_pr_t* s, void** W, void** P, void** partial);
 /* Replace the current pupil estimate by an unshifted N x N complex128 pupil (NULL: the ideal
  * pupil again).  Lets a caller re-seed single iterations (parity tests) or warm-start. */
 int pyotf_b200_pr_set_pupil(pyotf_pr_t* s, const void* pupil_c128_dev, void* stream);

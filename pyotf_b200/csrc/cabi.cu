@@ -282,8 +282,7 @@ int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev,
     PYOTF_REQUIRE(params && z_dev && data_dev && out, "pr_create: null argument");
     PYOTF_REQUIRE(nz > 0 && nz_total >= nz, "pr_create: bad nz / nz_total");
     PYOTF_REQUIRE(data_dtype == PYOTF_F32 || data_dtype == PYOTF_F64, "pr_create: bad data dtype");
-    PYOTF_REQUIRE(params->size == 32 || params->size == 64 || params->size == 128 || params->size == 256,
-                  "pr_create: size must be one of 32, 64, 128, 256 on the fused path");
+    PYOTF_REQUIRE(params->size >= 2 && params->size <= 16384, "pr_create: size must be in 2..16384");
     pyotf_hanser_params p = *params;
     p.vec_corr = PYOTF_VEC_NONE; p.condition = PYOTF_COND_NONE; p.support = -2;   // phaseretrieval.py:74-76
     pyotf_pr* s = new pyotf_pr();
@@ -305,7 +304,7 @@ int pyotf_b200_pr_destroy(pyotf_pr_t* s) {
     if (!s) return 0;
     cudaFree(s->z); cudaFree(s->data); cudaFree(s->pupil[0]); cudaFree(s->pupil[1]); cudaFree(s->partial);
     cudaFree(s->mse_part); cudaFree(s->sums); cudaFree(s->diffpart); cudaFree(s->mse); cudaFree(s->mse_diff);
-    cudaFree(s->pupil_diff); cudaFree(s->state); cudaFree(s->dtab);
+    cudaFree(s->pupil_diff); cudaFree(s->state); cudaFree(s->dtab); cudaFree(s->W); cudaFree(s->P);
     if (s->h_flags) { cudaFreeHost(s->h_flags); for (int i = 0; i < 4; ++i) cudaEventDestroy(s->ev[i]); }
     pyotf_b200_hanser_destroy(s->h);
     delete s;
@@ -319,6 +318,14 @@ int pyotf_b200_pr_info(const pyotf_pr_t* s, int* K, int* rows, int* f0, int* row
     if (f0) *f0 = s->h->f0;
     if (rows_per_cta) *rows_per_cta = s->M;
     if (nparts) *nparts = s->nparts;
+    return 0;
+}
+
+int pyotf_b200_pr_debug_buffers(const pyotf_pr_t* s, void** W, void** P, void** partial) {
+    PYOTF_REQUIRE(s, "pr_debug_buffers: null handle");
+    if (W) *W = s->W;
+    if (P) *P = s->P;
+    if (partial) *partial = s->partial;
     return 0;
 }
 

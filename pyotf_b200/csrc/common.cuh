@@ -65,7 +65,10 @@ struct pyotf_comm;
 // phase-retrieval state (K2); buffers are in the handle's dtype unless noted
 struct pyotf_pr {
     pyotf_hanser* h = nullptr;      // owned geometry (support = -2, vec_corr / condition = none)
-    int nz = 0, M = 0, nth = 256, nparts = 0, nblk = 0, cap_iters = 0;
+    int nz = 0, M = 0, nth = 256, nparts = 0, nmse = 0, nblk = 0, cap_iters = 0;
+    int generic = 0;                // 1: four-pass path (sizes outside the fused kernel's set)
+    void* W = nullptr;              // generic: [nz][K][N] complex
+    void* P = nullptr;              // generic: [nz][N][N] complex
     long long nz_total = 0;         // planes over all ranks of a z-sharded retrieval
     int cur = 0, applied = 0;       // pupil buffer holding the final / the last applied pupil
     int launched = 0;               // iterations enqueued by the last run

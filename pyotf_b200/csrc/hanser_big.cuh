@@ -37,6 +37,8 @@ template <int DIR, typename T, int L, int TI, bool POW2, bool LINE_MAJOR, class 
 __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nlines_total, F f) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ typename F::Line sline[TI];
+    if (f.skip()) return;                                     // e.g. phase retrieval already converged
+    typename F::Acc acc = F::acc_init();                      // per-thread accumulator of the store functor
     const int Lr = POW2 ? L : Lrt;
     const int pitch = Lr + 1;
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
@@ -91,27 +93,36 @@ __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nline
             int t = w / Lr, o = w - t * Lr;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            f.store(sline[t], o, res[(size_t)t * pitch + pos]);
+            f.store(sline[t], o, res[(size_t)t * pitch + pos], acc);
         }
     } else if (nlines == TI) {
         for (int w = threadIdx.x; w < TI * Lr; w += blockDim.x) {
             int o = w / TI, t = w - o * TI;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            f.store(sline[t], o, res[(size_t)t * pitch + pos]);
+            f.store(sline[t], o, res[(size_t)t * pitch + pos], acc);
         }
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int o = w / nlines, t = w - o * nlines;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            f.store(sline[t], o, res[(size_t)t * pitch + pos]);
+            f.store(sline[t], o, res[(size_t)t * pitch + pos], acc);
         }
     }
+    f.finish(acc);
 }
 
+// functors without a reduction / early exit
+struct NoAcc {
+    using Acc = int;
+    __device__ __forceinline__ static Acc acc_init() { return 0; }
+    __device__ __forceinline__ void finish(Acc) const {}
+    __device__ __forceinline__ bool skip() const { return false; }
+};
+
 // ---- pass A: line = (plane, iy), axis = kx --------------------------------------------------
-template <typename T> struct BigRow {
+template <typename T> struct BigRow : NoAcc {
     struct Line { int iy; double z; cplx<T>* w; };
     BigArgs<T> a;
     __device__ __forceinline__ Line info(long long line) const {
@@ -134,11 +145,11 @@ template <typename T> struct BigRow {
         if (a.pupilc) v = cmul(v, a.pupilc[off]);
         return v;
     }
-    __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v) const { d.w[o] = v; }   // x stays unshifted
+    __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v, int&) const { d.w[o] = v; }   // x stays unshifted
     __device__ __forceinline__ cplx<T> twiddle(int k) const { return a.tw[k]; }
 };
 // ---- pass B: line = (plane, x), axis = ky ---------------------------------------------------
-template <typename T> struct BigCol {
+template <typename T> struct BigCol : NoAcc {
     struct Line { const cplx<T>* w; cplx<T>* psfa; T* psfi; };
     BigArgs<T> a;
     __device__ __forceinline__ Line info(long long line) const {
@@ -157,7 +168,7 @@ template <typename T> struct BigCol {
         if (iy < 0 || iy >= a.K) return mk<T>(0, 0);
         return d.w[(size_t)iy * a.N];
     }
-    __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v) const {
+    __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v, int&) const {
         int ys = o + a.N / 2; if (ys >= a.N) ys -= a.N;            // fftshift
         const T sc = (T)a.scale;
         v = cscale(v, sc);

@@ -142,7 +142,7 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int
 // K1b launchers (hanser_big.cuh): any size, two line-FFT passes per plane chunk
 // ---------------------------------------------------------------------------------------
 template <int DIR, typename T, int L, bool POW2, bool LM, int TI, class F>
-int fft_lines_launch_ti(int Lr, long long nlines, F f, size_t smem, cudaStream_t s) {
+int fft_lines_launch_ti(int Lr, long long nlines, F f, size_t smem, cudaStream_t s, int* nblocks_out) {
     auto kern = fft_lines_kernel<DIR, T, L, TI, POW2, LM, F>;
     static thread_local size_t configured = 0;
     if (smem > configured) {
@@ -151,31 +151,32 @@ int fft_lines_launch_ti(int Lr, long long nlines, F f, size_t smem, cudaStream_t
     }
     long long nblocks = (nlines + TI - 1) / TI;
     PYOTF_REQUIRE(nblocks > 0 && nblocks < (1ll << 31), "hanser_psf: bad grid");
+    if (nblocks_out) *nblocks_out = (int)nblocks;
     kern<<<(unsigned)nblocks, 256, smem, s>>>(Lr, nlines, f);
     PYOTF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 template <int DIR, typename T, int L, bool POW2, bool LM, class F>
-int fft_lines_launch_l(int Lr, long long nlines, F f, int smem_limit, cudaStream_t s) {
+int fft_lines_launch_l(int Lr, long long nlines, F f, int smem_limit, cudaStream_t s, int* nblocks_out) {
     auto need = [&](int ti) { return sizeof(cplx<T>) * ((size_t)Lr + (size_t)ti * (Lr + 1) * (POW2 ? 1 : 2)); };
     const size_t soft = (size_t)smem_limit / 2 - 1024;
     if (need(16) <= soft || (need(8) > (size_t)smem_limit && need(16) <= (size_t)smem_limit))
-        return fft_lines_launch_ti<DIR, T, L, POW2, LM, 16>(Lr, nlines, f, need(16), s);
+        return fft_lines_launch_ti<DIR, T, L, POW2, LM, 16>(Lr, nlines, f, need(16), s, nblocks_out);
     if (need(8) <= soft || (need(4) > (size_t)smem_limit && need(8) <= (size_t)smem_limit))
-        return fft_lines_launch_ti<DIR, T, L, POW2, LM, 8>(Lr, nlines, f, need(8), s);
+        return fft_lines_launch_ti<DIR, T, L, POW2, LM, 8>(Lr, nlines, f, need(8), s, nblocks_out);
     PYOTF_REQUIRE(need(4) <= (size_t)smem_limit, "hanser_psf: size too large for the shared-memory line FFT");
-    return fft_lines_launch_ti<DIR, T, L, POW2, LM, 4>(Lr, nlines, f, need(4), s);
+    return fft_lines_launch_ti<DIR, T, L, POW2, LM, 4>(Lr, nlines, f, need(4), s, nblocks_out);
 }
 
 template <int DIR, typename T, bool LM, class F>
-int fft_lines_launch(int L, long long nlines, F f, int smem_limit, cudaStream_t s) {
+int fft_lines_launch(int L, long long nlines, F f, int smem_limit, cudaStream_t s, int* nblocks_out = nullptr) {
     switch (L) {
-#define PYOTF_CASE(LL) case LL: return fft_lines_launch_l<DIR, T, LL, true, LM>(L, nlines, f, smem_limit, s);
+#define PYOTF_CASE(LL) case LL: return fft_lines_launch_l<DIR, T, LL, true, LM>(L, nlines, f, smem_limit, s, nblocks_out);
         PYOTF_CASE(2) PYOTF_CASE(4) PYOTF_CASE(8) PYOTF_CASE(16) PYOTF_CASE(32) PYOTF_CASE(64) PYOTF_CASE(128)
         PYOTF_CASE(256) PYOTF_CASE(512) PYOTF_CASE(1024) PYOTF_CASE(2048)
 #undef PYOTF_CASE
-        default: return fft_lines_launch_l<DIR, T, 0, false, LM>(L, nlines, f, smem_limit, s);
+        default: return fft_lines_launch_l<DIR, T, 0, false, LM>(L, nlines, f, smem_limit, s, nblocks_out);
     }
 }
 
@@ -203,8 +204,8 @@ int hanser_launch_big(const pyotf_hanser* h, const double* z, int nz, const void
                 a.psfi = psfi ? (T*)psfi + ((size_t)b * nz + z0) * plane : nullptr;
                 a.N = N; a.K = K; a.f0 = h->f0; a.nzc = nc; a.accumulate = v > 0;
                 a.scale = 1.0 / ((double)N * (double)N);           // numpy ifftn "backward" normalisation
-                rc = fft_lines_launch<1, T, true>(N, (long long)nc * K, BigRow<T>{a}, smem_limit, s);
-                if (!rc) rc = fft_lines_launch<1, T, false>(N, (long long)nc * N, BigCol<T>{a}, smem_limit, s);
+                { BigRow<T> fa; fa.a = a; rc = fft_lines_launch<1, T, true>(N, (long long)nc * K, fa, smem_limit, s); }
+                if (!rc) { BigCol<T> fb; fb.a = a; rc = fft_lines_launch<1, T, false>(N, (long long)nc * N, fb, smem_limit, s); }
             }
         }
     cudaFreeAsync(W, s);

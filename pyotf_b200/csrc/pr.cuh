@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
 // the buffer a z-sharded run all-reduces across ranks.
 template <typename T>
 __global__ void pr_reduce_kernel(const cplx<T>* __restrict__ partial, const double* __restrict__ mse_part, int nparts,
-                                 int KK, double2* __restrict__ sums, const PrState* __restrict__ state) {
+                                 int nmse, int KK, double2* __restrict__ sums, const PrState* __restrict__ state) {
     if (state->stopped) return;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < KK) {
@@ -282,13 +282,14 @@ __global__ void pr_reduce_kernel(const cplx<T>* __restrict__ partial, const doub
     }
     if (p == KK) {
         double s = 0.0;
-        for (int q = 0; q < nparts; ++q) s += mse_part[q];
+        for (int q = 0; q < nmse; ++q) s += mse_part[q];
         sums[KK] = make_double2(s, 0.0);
     }
 }
 
 struct PrFinalArgs {
     int iter, K, nparts;
+    int nmse;               // entries of mse_part (one per CTA of the kernel that compared model and data)
     int cur;                // which pupil buffer holds the pupil this iteration applied
     int phase_only, last_iter;
     double npix_total;      // nz_total * N * N   (mean of the squared error)
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(256) pr_finalize_kernel(PrFinalArgs a, const T
     if (tid < 32) {
         double s;
         if (a.nparts == 0) s = reinterpret_cast<const double2*>(partial)[KK].x;
-        else s = warp_sum_fixed(mse_part, a.nparts, 1, tid);
+        else s = warp_sum_fixed(mse_part, a.nmse, 1, tid);
         const double new_mse = s / a.npix_total;
         double md = nan(""), pd = nan("");
         if (a.iter > 0) {
@@ -438,7 +439,7 @@ __global__ void pr_unpack_pupil_kernel(int N, int K, int f0, const cplx<T>* __re
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * N) return;
     int y = idx / N, x = idx - y * N;
-    int fy = y < N / 2 ? y : y - N, fx = x < N / 2 ? x : x - N;
+    int fy = y < (N + 1) / 2 ? y : y - N, fx = x < (N + 1) / 2 ? x : x - N;   // fftfreq order, any N
     int iy = fy - f0, ix = fx - f0;
     double2 v = make_double2(0.0, 0.0);
     if (iy >= 0 && iy < K && ix >= 0 && ix < K) { cplx<T> s = src[iy * K + ix]; v = make_double2((double)s.x, (double)s.y); }

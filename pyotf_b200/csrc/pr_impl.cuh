@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "pr.cuh"
+#include "pr_big.cuh"
 
 namespace pyotf {
 
@@ -89,8 +90,16 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
     int smem_limit = 0, sms = 0;
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const size_t KK = (size_t)h->K * h->K, KKP = (size_t)h->KR * h->K, npix = (size_t)s->nz * h->N * h->N;
     s->nth = 256;
-    if (want_rows == 0 && h->N == 256 && sizeof(T) == 4 &&
+    s->generic = !(h->N == 32 || h->N == 64 || h->N == 128 || h->N == 256) || want_rows == 1;
+    if (s->generic) {
+        // four line-FFT passes per iteration (pr_big.cuh): one partial pupil per plane
+        s->M = 0; s->nparts = s->nz;
+        s->nmse = 0;                                   // set by every pass-B launch (its grid size)
+        PYOTF_CUDA_OK(cudaMalloc(&s->W, (size_t)s->nz * h->K * h->N * sizeof(cplx<T>)));
+        PYOTF_CUDA_OK(cudaMalloc(&s->P, npix * sizeof(cplx<T>)));
+    } else if (want_rows == 0 && h->N == 256 && sizeof(T) == 4 &&
         HanserSmem<256, 64, T, 512>::bytes(h->KP) <= (size_t)smem_limit) {
         s->M = 64; s->nth = 512;      // one wide CTA per SM (16 warps): measured faster than two narrow ones
     } else if (want_rows < 0) {
@@ -99,15 +108,18 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
     } else {
         s->M = pr_pick_rows<T>(h, s->nz, smem_limit, sms, want_rows);
     }
-    PYOTF_REQUIRE(s->M != 0, "pr_create: no rows-per-CTA choice fits shared memory at this size / dtype");
-    s->nparts = s->nz * (h->N / s->M);
-    const size_t KK = (size_t)h->K * h->K, KKP = (size_t)h->KR * h->K, npix = (size_t)s->nz * h->N * h->N;
+    if (!s->generic) {
+        PYOTF_REQUIRE(s->M != 0, "pr_create: no rows-per-CTA choice fits shared memory at this size / dtype");
+        s->nparts = s->nz * (h->N / s->M);
+        s->nmse = s->nparts;
+    }
     s->nblk = (int)((KK + PR_FIN_PIX - 1) / PR_FIN_PIX);
     PYOTF_CUDA_OK(cudaMalloc(&s->data, npix * sizeof(T)));
     PYOTF_CUDA_OK(cudaMalloc(&s->pupil[0], KKP * sizeof(cplx<T>)));
     PYOTF_CUDA_OK(cudaMalloc(&s->pupil[1], KKP * sizeof(cplx<T>)));
     PYOTF_CUDA_OK(cudaMalloc(&s->partial, (size_t)s->nparts * KK * sizeof(cplx<T>)));
-    PYOTF_CUDA_OK(cudaMalloc(&s->mse_part, (size_t)s->nparts * sizeof(double)));
+    // fused: one squared-error partial per CTA of the plane kernel; generic: per CTA of pass B (>= 4 lines each)
+    PYOTF_CUDA_OK(cudaMalloc(&s->mse_part, (s->generic ? (size_t)s->nz * h->N / 4 + 1 : (size_t)s->nparts) * sizeof(double)));
     PYOTF_CUDA_OK(cudaMalloc(&s->sums, (KK + 1) * sizeof(double2)));
     PYOTF_CUDA_OK(cudaMalloc(&s->diffpart, (size_t)4 * s->nblk * sizeof(double)));
     PYOTF_CUDA_OK(cudaMalloc(&s->state, sizeof(PrState)));
@@ -154,6 +166,34 @@ template <typename T> int pr_get_pupil(const pyotf_pr* s, int which, void* out_c
     return 0;
 }
 
+// one iteration's transforms on the four-pass path (pr_big.cuh); the finalize kernel follows as usual
+template <typename T> int pr_generic_passes(pyotf_pr* s, int cur, cudaStream_t st) {
+    const pyotf_hanser* h = s->h;
+    int smem_limit = 0;
+    PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const int N = h->N, K = h->K;
+    BigArgs<T> ba;
+    ba.kzc = h->kzc; ba.ampc = (const T*)h->ampc; ba.pupilc = (const cplx<T>*)s->pupil[cur]; ba.tw = (const cplx<T>*)h->tw;
+    ba.z = s->z; ba.W = (cplx<T>*)s->W; ba.psfa = nullptr; ba.psfi = nullptr;
+    ba.N = N; ba.K = K; ba.f0 = h->f0; ba.nzc = s->nz; ba.accumulate = 0; ba.scale = 1.0;
+    BigRow<T> fa; fa.a = ba;
+    int rc = fft_lines_launch<1, T, true>(N, (long long)s->nz * K, fa, smem_limit, st);                          // A
+    if (rc) return rc;
+    PrBigArgs<T> pa;
+    pa.kzc = h->kzc; pa.z = s->z; pa.data = (const T*)s->data; pa.W = (cplx<T>*)s->W; pa.P = (cplx<T>*)s->P;
+    pa.partial = (cplx<T>*)s->partial; pa.mse_part = s->mse_part; pa.tw = (const cplx<T>*)h->tw;
+    pa.state = (const PrState*)s->state; pa.N = N; pa.K = K; pa.f0 = h->f0;
+    pa.scale = 1.0 / ((double)N * (double)N);
+    PrColInv<T> fb; fb.a = pa;
+    rc = fft_lines_launch<1, T, false>(N, (long long)s->nz * N, fb, smem_limit, st, &s->nmse);                   // B
+    if (rc) return rc;
+    PrColFwd<T> fc; fc.a = pa;
+    rc = fft_lines_launch<-1, T, false>(N, (long long)s->nz * N, fc, smem_limit, st);                            // C
+    if (rc) return rc;
+    PrRowFwd<T> fd; fd.a = pa;
+    return fft_lines_launch<-1, T, true>(N, (long long)s->nz * K, fd, smem_limit, st);                           // D
+}
+
 int comm_allreduce_f64(pyotf_comm* c, double* buf, long long n, cudaStream_t st);
 
 template <typename T>
@@ -188,11 +228,11 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
             if (s->h_flags[slot]) break;
         }
         const int cur = (start + i) & 1;
-        int rc = pr_plane_launch<T>(s, cur, st);
+        int rc = s->generic ? pr_generic_passes<T>(s, cur, st) : pr_plane_launch<T>(s, cur, st);
         if (rc) return rc;
-        fa.iter = i; fa.cur = cur; fa.last_iter = i == max_iters - 1;
+        fa.iter = i; fa.cur = cur; fa.last_iter = i == max_iters - 1; fa.nmse = s->nmse;
         if (comm) {
-            pr_reduce_kernel<T><<<(KK + 1 + 255) / 256, 256, 0, st>>>((const cplx<T>*)s->partial, s->mse_part, s->nparts, KK,
+            pr_reduce_kernel<T><<<(KK + 1 + 255) / 256, 256, 0, st>>>((const cplx<T>*)s->partial, s->mse_part, s->nparts, s->nmse, KK,
                                                                      (double2*)s->sums, (const PrState*)s->state);
             PYOTF_CUDA_OK(cudaGetLastError());
             rc = comm_allreduce_f64(comm, (double*)s->sums, 2ll * (KK + 1), st);

@@ -53,6 +53,7 @@ def retrieve_phase(data, params, max_iters=200, pupil_tol=1e-8, mse_tol=1e-8, ph
         the dict is updated in place like the reference does)
     max_iters, pupil_tol, mse_tol, phase_only : as in the reference
     precision : "fp32" | "fp64" kernel arithmetic (keyword-only extension)
+    rows_per_cta : tuning knob of the fused kernel (0 = auto; 1 forces the four-pass path K2b)
     comm, nz_total : z-sharded multi-GPU retrieval -- ``data`` holds this rank's planes,
         ``params["zrange"]`` their positions, ``nz_total`` the plane count over all ranks and
         ``comm`` a ``pyotf_b200._engine.Comm`` (one all-reduce per iteration)
@@ -62,9 +63,7 @@ def retrieve_phase(data, params, max_iters=200, pupil_tol=1e-8, mse_tol=1e-8, ph
     assert data.ndim == 3, "Data doesn't have enough dims"
     params.update(dict(vec_corr="none", condition="none", zsize=data.shape[0], size=data.shape[-1]))
     model = HanserPSF(**params, precision=precision)
-    if model.size not in (32, 64, 128, 256):
-        raise NotImplementedError("retrieve_phase: the fused CUDA path covers sizes 32, 64, 128 and 256 "
-                                  "(there is no CPU fallback)")
+    model._check_size()   # 32..256 powers of two: fused kernel K2; every other size: the four-pass path K2b
     torch = _engine._torch()
     want = torch.float32 if model.precision == "fp32" else torch.float64
     if not isinstance(data, np.ndarray) and hasattr(data, "is_cuda"):

@@ -208,3 +208,39 @@ def test_integration_twin_400_iterations_recovers_the_pupil():
     zd = r.fit_to_zernikes(15)
     np.testing.assert_allclose(zd.pcoefs[4:], g["pcoefs"], rtol=1e-6, atol=1e-8)                    # test_zernike_modes_phase
     np.testing.assert_allclose(zd.mcoefs[4:], g["mcoefs"], rtol=1e-6, atol=1e-8)                    # test_zernike_modes_mag
+
+
+@pytest.mark.parametrize("size,nz,precision", [(64, 5, "fp64"), (128, 4, "fp64"), (128, 4, "fp32"), (100, 3, "fp64"),
+                                               (45, 4, "fp64"), (63, 5, "fp64"), (512, 3, "fp64"), (512, 3, "fp32")])
+def test_generic_size_path_vs_oracle(size, nz, precision):
+    """K2b, the four-pass path for sizes outside {32, 64, 128, 256} (forced with rows_per_cta=1 at 64 / 128 so
+    that it is also checked against the fused kernel).
+
+    The planes are offset from z = 0: with the ideal start pupil the in-focus amplitude is exactly real and,
+    for sizes such as 45 or 63, exactly zero on whole columns, where angle(PSFa) is decided by the rounding
+    noise of whichever FFT computed it (the reference's own result is arbitrary there)."""
+    from oracle import pyotf_oracle as orc
+    from pyotf_b200.phaseretrieval import retrieve_phase
+
+    rng = np.random.default_rng(size)
+    z = orc.default_zrange(nz, OPT["zres"]) + 41.0
+    pupil = orc.aberrated_pupil(OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], size, rng.random(15) * 0.1, rng.random(15))
+    data = orc.psfi(orc.hanser_psfa(OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], size, z, "none", "none", pupil)) * 1e4
+    params = dict(wl=OPT["wl"], na=OPT["na"], ni=OPT["ni"], res=OPT["res"], zrange=z)
+    iters = 8
+    o = orc.retrieve_phase_loop(data, OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], zrange=z, max_iters=iters,
+                                pupil_tol=0, mse_tol=0)
+    r = retrieve_phase(data, dict(params), iters, 0, 0, precision=precision, rows_per_cta=1)
+    tol = 1e-11 if precision == "fp64" else 1e-5
+    assert len(r.mse) == iters
+    assert rel_l2(r.mse, o["mse"]) <= tol
+    assert rel_l2(r.pupil, o["pupil"]) <= (tol if precision == "fp64" else 2e-5)
+    assert rel_l2(r.model.PSFi, o["psfi"]) <= tol
+    if size in (64, 128):
+        f = retrieve_phase(data, dict(params), iters, 0, 0, precision=precision)       # fused kernel
+        assert rel_l2(r.pupil, f.pupil) <= (1e-12 if precision == "fp64" else 2e-5)
+    # early stop decides on the same iteration as the reference loop
+    o2 = orc.retrieve_phase_loop(data, OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], zrange=z, max_iters=40,
+                                 pupil_tol=3e-3, mse_tol=0)
+    r2 = retrieve_phase(data, dict(params), 40, 3e-3, 0, precision=precision, rows_per_cta=1)
+    assert len(r2.mse) == o2["iters"]
