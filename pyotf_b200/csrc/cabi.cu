@@ -290,7 +290,9 @@ int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev,
     if (rc) { delete s; return rc; }
     s->nz = nz; s->nz_total = nz_total;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMalloc(&s->z, sizeof(double) * nz);
+    keep_scratch_pool();
+    s->stream = st;
+    cudaError_t e = cudaMallocAsync(&s->z, sizeof(double) * nz, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(s->z, z_dev, sizeof(double) * nz, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) { set_error(std::string("pr_create: ") + cudaGetErrorString(e)); pyotf_b200_pr_destroy(s); return 2; }
     rc = p.dtype == PYOTF_F32 ? pr_setup<float>(s, data_dev, data_dtype, rows_per_cta, st)
@@ -302,9 +304,10 @@ int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev,
 
 int pyotf_b200_pr_destroy(pyotf_pr_t* s) {
     if (!s) return 0;
-    cudaFree(s->z); cudaFree(s->data); cudaFree(s->pupil[0]); cudaFree(s->pupil[1]); cudaFree(s->partial);
-    cudaFree(s->mse_part); cudaFree(s->sums); cudaFree(s->diffpart); cudaFree(s->mse); cudaFree(s->mse_diff);
-    cudaFree(s->pupil_diff); cudaFree(s->state); cudaFree(s->dtab); cudaFree(s->W); cudaFree(s->P);
+    cudaStream_t st = s->stream;
+    void* bufs[] = {s->z, s->data, s->pupil[0], s->pupil[1], s->partial, s->mse_part, s->sums, s->diffpart, s->mse,
+                    s->mse_diff, s->pupil_diff, s->state, s->dtab, s->W, s->P};
+    for (void* b : bufs) if (b) cudaFreeAsync(b, st);         // stream-ordered: returns to the cached pool
     if (s->h_flags) { cudaFreeHost(s->h_flags); for (int i = 0; i < 4; ++i) cudaEventDestroy(s->ev[i]); }
     pyotf_b200_hanser_destroy(s->h);
     delete s;

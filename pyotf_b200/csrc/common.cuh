@@ -82,6 +82,7 @@ struct pyotf_pr {
     double *mse = nullptr, *mse_diff = nullptr, *pupil_diff = nullptr;   // [cap_iters]
     void* dtab = nullptr;           // [nz][dtab_size] defocus tables of this stack (built once)
     void* state = nullptr;          // PrState
+    cudaStream_t stream = nullptr;  // creation stream: the state's buffers are stream-ordered allocations on it
     int* h_flags = nullptr;         // pinned: early-stop polling
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

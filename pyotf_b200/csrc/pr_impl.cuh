@@ -87,6 +87,8 @@ template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, cudaStream
 
 template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype, int want_rows, cudaStream_t st) {
     pyotf_hanser* h = s->h;
+    keep_scratch_pool();
+    s->stream = st;
     int smem_limit = 0, sms = 0;
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -97,8 +99,8 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
         // four line-FFT passes per iteration (pr_big.cuh): one partial pupil per plane
         s->M = 0; s->nparts = s->nz;
         s->nmse = 0;                                   // set by every pass-B launch (its grid size)
-        PYOTF_CUDA_OK(cudaMalloc(&s->W, (size_t)s->nz * h->K * h->N * sizeof(cplx<T>)));
-        PYOTF_CUDA_OK(cudaMalloc(&s->P, npix * sizeof(cplx<T>)));
+        PYOTF_CUDA_OK(cudaMallocAsync(&s->W, (size_t)s->nz * h->K * h->N * sizeof(cplx<T>), st));
+        PYOTF_CUDA_OK(cudaMallocAsync(&s->P, npix * sizeof(cplx<T>), st));
     } else if (want_rows == 0 && h->N == 256 && sizeof(T) == 4 &&
         HanserSmem<256, 64, T, 512>::bytes(h->KP) <= (size_t)smem_limit) {
         s->M = 64; s->nth = 512;      // one wide CTA per SM (16 warps): measured faster than two narrow ones
@@ -114,15 +116,15 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
         s->nmse = s->nparts;
     }
     s->nblk = (int)((KK + PR_FIN_PIX - 1) / PR_FIN_PIX);
-    PYOTF_CUDA_OK(cudaMalloc(&s->data, npix * sizeof(T)));
-    PYOTF_CUDA_OK(cudaMalloc(&s->pupil[0], KKP * sizeof(cplx<T>)));
-    PYOTF_CUDA_OK(cudaMalloc(&s->pupil[1], KKP * sizeof(cplx<T>)));
-    PYOTF_CUDA_OK(cudaMalloc(&s->partial, (size_t)s->nparts * KK * sizeof(cplx<T>)));
+    PYOTF_CUDA_OK(cudaMallocAsync(&s->data, npix * sizeof(T), st));
+    PYOTF_CUDA_OK(cudaMallocAsync(&s->pupil[0], KKP * sizeof(cplx<T>), st));
+    PYOTF_CUDA_OK(cudaMallocAsync(&s->pupil[1], KKP * sizeof(cplx<T>), st));
+    PYOTF_CUDA_OK(cudaMallocAsync(&s->partial, (size_t)s->nparts * KK * sizeof(cplx<T>), st));
     // fused: one squared-error partial per CTA of the plane kernel; generic: per CTA of pass B (>= 4 lines each)
-    PYOTF_CUDA_OK(cudaMalloc(&s->mse_part, (s->generic ? (size_t)s->nz * h->N / 4 + 1 : (size_t)s->nparts) * sizeof(double)));
-    PYOTF_CUDA_OK(cudaMalloc(&s->sums, (KK + 1) * sizeof(double2)));
-    PYOTF_CUDA_OK(cudaMalloc(&s->diffpart, (size_t)4 * s->nblk * sizeof(double)));
-    PYOTF_CUDA_OK(cudaMalloc(&s->state, sizeof(PrState)));
+    PYOTF_CUDA_OK(cudaMallocAsync(&s->mse_part, (s->generic ? (size_t)s->nz * h->N / 4 + 1 : (size_t)s->nparts) * sizeof(double), st));
+    PYOTF_CUDA_OK(cudaMallocAsync(&s->sums, (KK + 1) * sizeof(double2), st));
+    PYOTF_CUDA_OK(cudaMallocAsync(&s->diffpart, (size_t)4 * s->nblk * sizeof(double), st));
+    PYOTF_CUDA_OK(cudaMallocAsync(&s->state, sizeof(PrState), st));
     PYOTF_CUDA_OK(cudaMemsetAsync(s->state, 0, sizeof(PrState), st));
     const unsigned nb = (unsigned)((npix + 255) / 256);
     if (data_dtype == PYOTF_F32) pr_convert_data_kernel<float, T><<<nb, 256, 0, st>>>((const float*)data, (T*)s->data, npix);
@@ -133,7 +135,7 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
     PYOTF_CUDA_OK(cudaGetLastError());
     // the defocus tables depend on the plane positions only: built once per stack
     if (const int ntab = hanser_ntab<T>(h)) {
-        PYOTF_CUDA_OK(cudaMalloc(&s->dtab, (size_t)s->nz * ntab * sizeof(cplx<T>)));
+        PYOTF_CUDA_OK(cudaMallocAsync(&s->dtab, (size_t)s->nz * ntab * sizeof(cplx<T>), st));
         int rc = hanser_build_dtabs<T>(h, s->z, s->nz, false, (cplx<T>*)s->dtab, st);
         if (rc) return rc;
     }
@@ -202,11 +204,11 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
     const pyotf_hanser* h = s->h;
     const int KK = h->K * h->K;
     if (s->cap_iters < max_iters) {
-        cudaFree(s->mse); cudaFree(s->mse_diff); cudaFree(s->pupil_diff);
+        cudaFreeAsync(s->mse, st); cudaFreeAsync(s->mse_diff, st); cudaFreeAsync(s->pupil_diff, st);
         s->mse = s->mse_diff = s->pupil_diff = nullptr; s->cap_iters = 0;
-        PYOTF_CUDA_OK(cudaMalloc(&s->mse, sizeof(double) * max_iters));
-        PYOTF_CUDA_OK(cudaMalloc(&s->mse_diff, sizeof(double) * max_iters));
-        PYOTF_CUDA_OK(cudaMalloc(&s->pupil_diff, sizeof(double) * max_iters));
+        PYOTF_CUDA_OK(cudaMallocAsync(&s->mse, sizeof(double) * max_iters, st));
+        PYOTF_CUDA_OK(cudaMallocAsync(&s->mse_diff, sizeof(double) * max_iters, st));
+        PYOTF_CUDA_OK(cudaMallocAsync(&s->pupil_diff, sizeof(double) * max_iters, st));
         s->cap_iters = max_iters;
     }
     constexpr int CHK = 8, NSLOT = 4;

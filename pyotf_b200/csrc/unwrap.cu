@@ -67,7 +67,11 @@ extern "C" int pyotf_b200_unwrap_phase_2d(const double* in, double* out, int ny,
             if (x + 1 < nx) edges.push_back({rel[i] + rel[i + 1], i, i + 1});
             if (y + 1 < ny) edges.push_back({rel[i] + rel[i + nx], i, i + nx});
         }
-    std::stable_sort(edges.begin(), edges.end(), [](const Edge& p, const Edge& q) { return p.r < q.r; });
+    // ascending reliability, ties in generation order.  Most edges of a retrieved pupil lie in the zero
+    // region outside the aperture (reliability exactly 0): they are moved to the front unsorted and only the
+    // rest is sorted -- the same order a stable sort of everything would give.
+    auto mid = std::stable_partition(edges.begin(), edges.end(), [](const Edge& e) { return e.r == 0.0; });
+    std::stable_sort(mid, edges.end(), [](const Edge& p, const Edge& q) { return p.r < q.r; });
     UnionFind uf(n);
     for (const Edge& e : edges) {
         int pa, pb;
