@@ -123,10 +123,12 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int
     const int cand[3] = {64, 32, 16};
     static const int forced = [] { const char* e = getenv("PYOTF_B200_K1_ROWS"); return e ? atoi(e) : 0; }();   // tuning knob
     if (forced && forced <= N && hanser_smem_for<T, N>(forced, a.KP) <= (size_t)smem_limit) pick = forced;
-    for (int pass = 0; pass < 2 && !pick; ++pass)
+    // 64 or 32 rows per CTA, two CTAs per SM if the working set allows, else one; 16 rows only as a last
+    // resort (its radix-16 fold spills registers badly: measured 20x slower)
+    for (int pass = 0; pass < 3 && !pick; ++pass)
         for (int i = 0; i < 3 && !pick; ++i) {
             int M = cand[i];
-            if (M > N) continue;
+            if (M > N || (pass < 2 && M == 16 && N > 16)) continue;
             size_t need = hanser_smem_for<T, N>(M, a.KP);
             size_t lim = pass == 0 ? (size_t)(smem_limit / 2 - 1024) : (size_t)smem_limit;
             if (need <= lim) pick = M;

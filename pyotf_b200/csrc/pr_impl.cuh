@@ -27,14 +27,21 @@ template <typename T> int pr_pick_rows(const pyotf_hanser* h, int nz, int smem_l
         return 0;
     }
     int pick = 0;
-    for (int pass = 0; pass < 2 && !pick; ++pass)
+    // as for K1: 16 rows per CTA only when nothing else fits (register spills)
+    for (int pass = 0; pass < 3 && !pick; ++pass)
         for (int i = 0; i < 3 && !pick; ++i) {
             int M = cand[i];
-            if (M > h->N) continue;
+            if (M > h->N || (pass < 2 && M == 16 && h->N > 16)) continue;
             size_t lim = pass == 0 ? (size_t)(smem_limit / 2 - 1024) : (size_t)smem_limit;
             if (pr_smem_for<T>(h->N, M, h->KP) <= lim) pick = M;
         }
-    while (pick > 32 && nz * (h->N / pick) < sm_count) pick /= 2;
+    // short stack: fewer rows per CTA (more CTAs) only while everything still fits one wave
+    while (pick > 32 && nz * (h->N / pick) < sm_count) {
+        const int half = pick / 2;
+        const int per_sm = pr_smem_for<T>(h->N, half, h->KP) <= (size_t)(smem_limit / 2 - 1024) ? 2 : 1;
+        if (nz * (h->N / half) > sm_count * per_sm) break;
+        pick = half;
+    }
     return pick;
 }
 
