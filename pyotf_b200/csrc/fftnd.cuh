@@ -140,7 +140,45 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
     }
 
     // ---- load (coalesced along the contiguous direction), input shift folded in ----
-    if (contiguous) {
+    // full power-of-two tiles: every thread issues all of its loads before the first shared-memory
+    // store, so TI*L/256 (16 at L = 256) requests per thread are in flight -- the passes are bound by
+    // memory-level parallelism, not by bandwidth
+    constexpr bool FAST = POW2 && (TI * (POW2 ? L : 1)) % 256 == 0 && (TI * (POW2 ? L : 1)) / 256 <= 32;
+    bool fast = false;
+    if constexpr (FAST) fast = nlines == TI && blockDim.x == 256;
+    if constexpr (FAST) {
+        if (fast) {
+            constexpr int PER = TI * L / 256;
+            cplx<T> v[PER];
+            if (contiguous) {
+#pragma unroll
+                for (int k = 0; k < PER; ++k) v[k] = load_as_cplx<TIN, T>(src, base + threadIdx.x + 256 * k);   // lines are back to back
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    const int w = threadIdx.x + 256 * k;
+                    const int t = w / L, l = w % L;
+                    int i = l - p.in_shift; if (i < 0) i += L;
+                    tile[(size_t)t * pitch + i] = v[k];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    const int w = threadIdx.x + 256 * k;
+                    const int l = w / TI, t = w % TI;
+                    v[k] = load_as_cplx<TIN, T>(src, base + t + l * stride_l);
+                }
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    const int w = threadIdx.x + 256 * k;
+                    const int l = w / TI, t = w % TI;
+                    int i = l - p.in_shift; if (i < 0) i += L;
+                    tile[(size_t)t * pitch + i] = v[k];
+                }
+            }
+        }
+    }
+    if (fast) {
+    } else if (contiguous) {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int t = w / Lr, l = w - t * Lr;
             int i = l - p.in_shift; if (i < 0) i += Lr;       // src index l lands at x_in[i]
@@ -179,6 +217,20 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
     }
     // ---- store, output shift folded in ----
     const cplx<T>* res = POW2 ? tile : tile2;
+    if constexpr (FAST) {
+        if (fast) {
+            constexpr int PER = TI * L / 256;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int w = threadIdx.x + 256 * k;
+                const int t = contiguous ? w / L : w % TI, l = contiguous ? w % L : w / TI;
+                int o = l - p.out_shift; if (o < 0) o += L;
+                const int pos = digit_reversed_pos<L>(o);
+                dst[base + t * stride_t + l * stride_l] = cscale(res[(size_t)t * pitch + pos], scale);
+            }
+            return;
+        }
+    }
     if (contiguous) {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int t = w / Lr, l = w - t * Lr;                    // l = destination index
