@@ -28,6 +28,14 @@ struct PrState {
     int pad;
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; it must call pdl_wait() before
+// touching anything the predecessor writes, and the predecessor lets it go with pdl_launch_dependents().
+// Both are no-ops for ordinary launches.  The PR loop uses them to overlap each kernel's launch latency and
+// prologue (twiddles, defocus-table staging) with the tail of the previous kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T> struct PrPlaneArgs {
     const double* kzc;          // [KR][K]
     const cplx<T>* pupilc;      // [KR][K] current pupil (compact, zero padded rows)
@@ -39,6 +47,7 @@ template <typename T> struct PrPlaneArgs {
     double* mse_part;           // [nz * R]
     const PrState* state;
     int K, KR, KP, f0, nz;
+    int pdl;                    // launched with programmatic stream serialization (host-side flag only)
 };
 
 // new_psf = sqrt(max(data, 0)) * exp(i angle(a))  (psqrt, phaseretrieval.py:79; :120-122), I = |a|^2.
@@ -73,7 +82,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
     using SM = HanserSmem<N, M, T, NTH>;
     constexpr int NT = SM::NT;
     constexpr int R = N / M;
-    if (a.state->stopped) return;
+    pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[NT / 32];
     cplx<T>* tws = reinterpret_cast<cplx<T>*>(smem_raw);
@@ -106,6 +115,10 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
     const int rl = (tid >> 5) / ncw;
     const bool colactive = rl < nrl && kx < K;
 
+    // everything above reads per-stack constants only; the pupil, the state word and the partial-pupil
+    // buffer belong to the previous finalize kernel until it has completed
+    pdl_wait();
+    if (a.state->stopped) return;
     __syncthreads();
     // ---------------- inverse: fold + columns ----------------
     {
@@ -333,6 +346,8 @@ __global__ void __launch_bounds__(256) pr_finalize_kernel(PrFinalArgs a, const T
     const int tid = threadIdx.x;
     const int px = tid & (PR_FIN_PIX - 1), lane = tid / PR_FIN_PIX;
     const int KK = a.K * a.K;
+    pdl_launch_dependents();
+    pdl_wait();
     if (state->stopped) return;
     // every CTA evaluates the scalars in the same fixed order, so all of them take the same branch
     if (tid < 32) {

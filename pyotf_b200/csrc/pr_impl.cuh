@@ -54,7 +54,17 @@ int pr_plane_launch_nmt(const PrPlaneArgs<T>& a, cudaStream_t s) {
         PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    kern<<<(unsigned)((N / M) * a.nz), NTH, smem, s>>>(a);
+    if (a.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((N / M) * a.nz)); cfg.blockDim = dim3(NTH); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PYOTF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
+    } else {
+        kern<<<(unsigned)((N / M) * a.nz), NTH, smem, s>>>(a);
+    }
     PYOTF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -75,9 +85,10 @@ template <typename T, int N> int pr_plane_launch_n(const pyotf_hanser* h, int M,
     return pr_plane_launch_nm<T, N, 16>(h, nth, a, s);
 }
 
-template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, cudaStream_t st) {
+template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, bool pdl, cudaStream_t st) {
     const pyotf_hanser* h = s->h;
     PrPlaneArgs<T> a;
+    a.pdl = pdl ? 1 : 0;
     a.kzc = h->kzc; a.pupilc = (const cplx<T>*)s->pupil[cur]; a.tw = (const cplx<T>*)h->tw; a.dtab = (const cplx<T>*)s->dtab; a.z = s->z;
     a.data = (const T*)s->data; a.partial = (cplx<T>*)s->partial; a.mse_part = s->mse_part; a.state = (const PrState*)s->state;
     a.K = h->K; a.KR = h->KR; a.KP = h->KP; a.f0 = h->f0; a.nz = s->nz;
@@ -108,9 +119,11 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
         s->nmse = 0;                                   // set by every pass-B launch (its grid size)
         PYOTF_CUDA_OK(cudaMallocAsync(&s->W, (size_t)s->nz * h->K * h->N * sizeof(cplx<T>), st));
         PYOTF_CUDA_OK(cudaMallocAsync(&s->P, npix * sizeof(cplx<T>), st));
-    } else if (want_rows == 0 && h->N == 256 && sizeof(T) == 4 &&
+    } else if (want_rows == 0 && h->N == 256 && sizeof(T) == 4 && 2 * (s->nz * 4) <= 3 * sms &&
         HanserSmem<256, 64, T, 512>::bytes(h->KP) <= (size_t)smem_limit) {
-        s->M = 64; s->nth = 512;      // one wide CTA per SM (16 warps): measured faster than two narrow ones
+        // short stacks (up to ~1.5 plane quarters per SM): one wide 512-thread CTA per SM is faster than two
+        // narrow ones (27.4 vs 36.3 us at 25 planes); long stacks prefer the narrow ones (68.6 vs 72.5 at 100)
+        s->M = 64; s->nth = 512;
     } else if (want_rows < 0) {
         want_rows = -want_rows; s->nth = 512;   // tuning knob: force the wide variant (256^2, M = 64 only)
         s->M = pr_pick_rows<T>(h, s->nz, smem_limit, sms, want_rows);
@@ -230,6 +243,9 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
     fa.pupil_tol = pupil_tol; fa.mse_tol = mse_tol;
     const int start = s->cur;
     int launched = 0;
+    // programmatic dependent launch for the single-GPU fused loop (kernels overlap their neighbours' tails)
+    static const bool no_pdl = getenv("PYOTF_B200_NO_PDL") != nullptr;
+    const bool use_pdl = !comm && !s->generic && !no_pdl;
     for (int i = 0; i < max_iters; ++i) {
         if (i % CHK == 0 && i >= 2 * CHK) {            // stay at most ~2*CHK iterations ahead of the device
             const int slot = (i / CHK - 2) % NSLOT;
@@ -237,7 +253,7 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
             if (s->h_flags[slot]) break;
         }
         const int cur = (start + i) & 1;
-        int rc = s->generic ? pr_generic_passes<T>(s, cur, st) : pr_plane_launch<T>(s, cur, st);
+        int rc = s->generic ? pr_generic_passes<T>(s, cur, st) : pr_plane_launch<T>(s, cur, use_pdl, st);
         if (rc) return rc;
         fa.iter = i; fa.cur = cur; fa.last_iter = i == max_iters - 1; fa.nmse = s->nmse;
         if (comm) {
@@ -252,9 +268,22 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
                                                                    s->mse, s->mse_diff, s->pupil_diff, (PrState*)s->state);
         } else {
             fa.nparts = s->nparts;
-            pr_finalize_kernel<T, cplx<T>><<<s->nblk, 256, 0, st>>>(fa, (const cplx<T>*)s->partial, s->mse_part, h->maskc,
-                                                                   (cplx<T>*)s->pupil[0], (cplx<T>*)s->pupil[1], s->diffpart,
-                                                                   s->mse, s->mse_diff, s->pupil_diff, (PrState*)s->state);
+            if (use_pdl) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)s->nblk); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                PYOTF_CUDA_OK(cudaLaunchKernelEx(&cfg, pr_finalize_kernel<T, cplx<T>>, fa, (const cplx<T>*)s->partial,
+                                                 (const double*)s->mse_part, (const unsigned char*)h->maskc,
+                                                 (cplx<T>*)s->pupil[0], (cplx<T>*)s->pupil[1], s->diffpart, s->mse,
+                                                 s->mse_diff, s->pupil_diff, (PrState*)s->state));
+            } else {
+                pr_finalize_kernel<T, cplx<T>><<<s->nblk, 256, 0, st>>>(fa, (const cplx<T>*)s->partial, s->mse_part, h->maskc,
+                                                                       (cplx<T>*)s->pupil[0], (cplx<T>*)s->pupil[1], s->diffpart,
+                                                                       s->mse, s->mse_diff, s->pupil_diff, (PrState*)s->state);
+            }
         }
         PYOTF_CUDA_OK(cudaGetLastError());
         ++launched;
