@@ -430,6 +430,24 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = best_ms / args.steps
     planes_per_s = nz * world / (ms_per_step * 1e-3)
+    # streaming mode (opt-in, pyotf_b200_hanser_set_overlap): consecutive launches overlap their tails
+    h.set_overlap(True)
+    stream_ms = None
+    for _ in range(20):
+        barrier()
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        stream_ms = ms if stream_ms is None else min(stream_ms, ms)
+    h.set_overlap(False)
+    if dist is not None:
+        t = torch.tensor([stream_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stream_ms = float(t.item())
+    stream_ms /= args.steps
 
     # ---- e2e through the public API: host zrange in, host PSFi (numpy) out, every step ----
     model = HanserPSF(precision=precision, **CFG1)
@@ -483,7 +501,12 @@ def run_ours(args):
                        "parallelism": f"z-shard x{world} (no collective)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "hanser_psf_kernel", "algorithmic_bytes_per_launch": alg_bytes},
+                         "kernel": "hanser_psf_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "streaming_mode": {"ms_per_step": stream_ms, "planes_per_s": nz * world / (stream_ms * 1e-3),
+                                            "achieved": alg_bytes / (stream_ms * 1e-3) / 1e9,
+                                            "frac": alg_bytes / (stream_ms * 1e-3) / 1e9 / peak,
+                                            "note": "opt-in pyotf_b200_hanser_set_overlap: back-to-back launches "
+                                                    "overlap (programmatic dependent launch); not the default API path"}},
             "clocks": clocks,
             "e2e": {"value": nz * world / e2e_s, "unit": "planes/s", "h2d_bytes_per_step": int(zr.nbytes),
                     "d2h_bytes_per_step": int(nz * N * N * esize), "ms_per_step": 1e3 * e2e_s,

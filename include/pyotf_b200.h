@@ -83,6 +83,13 @@ int pyotf_b200_hanser_psf(const pyotf_hanser_t* h, const double* z_dev, int nz, 
                           int batch, long long pupil_stride, void* psfa_out_dev, void* psfi_out_dev,
                           void* stream);
 
+/* Streaming mode for back-to-back single-stack launches with the ideal pupil.  enable = 1: the caller promises
+ * that z_dev is not written by the kernel that precedes a pyotf_b200_hanser_psf call in its stream (uploads by
+ * cudaMemcpy are fine).  Consecutive launches then overlap (programmatic dependent launch): the next stack's
+ * CTAs fill the SMs the previous launch leaves idle in its last wave; each launch still waits for its
+ * predecessor before its first store, so results and their order are unchanged.  Default 0. */
+int pyotf_b200_hanser_set_overlap(pyotf_hanser_t* h, int enable);
+
 /* Full-grid pupil coordinates for the API hooks (HanserPSF._gen_kr, otf.py:335-344):
  * kr, phi, kz as [size*size] float64, unshifted; any output may be NULL. */
 int pyotf_b200_hanser_kspace(double wl, double ni, double res, int size, double* kr_dev, double* phi_dev,

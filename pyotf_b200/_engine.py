@@ -75,6 +75,10 @@ class HanserHandle:
         except Exception:
             pass
 
+    def set_overlap(self, enable=True):
+        """Streaming mode: back-to-back `psf` launches overlap (see pyotf_b200_hanser_set_overlap)."""
+        _lib.check(_lib.load().pyotf_b200_hanser_set_overlap(self._h, int(bool(enable))))
+
     def tables(self):
         """(kz [K,K] f64, amp [nvec,K,K], mask [K,K] u8) device tensors -- for tests."""
         torch = _torch()

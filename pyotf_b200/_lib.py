@@ -41,6 +41,7 @@ PROTOTYPES = {
     "pyotf_b200_device_query": (_i, [_i, _ip, _ip, _ip, _ip]),
     "pyotf_b200_hanser_create": (_i, [C.POINTER(HanserParams), _vp, C.POINTER(_vp)]),
     "pyotf_b200_hanser_destroy": (_i, [_vp]),
+    "pyotf_b200_hanser_set_overlap": (_i, [_vp, _i]),
     "pyotf_b200_hanser_info": (_i, [_vp, _ip, _ip, _ip, _ip]),
     "pyotf_b200_hanser_tables": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "pyotf_b200_pupil_support": (_i, [_vp, _i, _ip, _vp]),

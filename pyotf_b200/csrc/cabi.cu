@@ -127,6 +127,12 @@ int pyotf_b200_hanser_destroy(pyotf_hanser_t* h) {
     return 0;
 }
 
+int pyotf_b200_hanser_set_overlap(pyotf_hanser_t* h, int enable) {
+    PYOTF_REQUIRE(h, "hanser_set_overlap: null handle");
+    h->overlap = enable ? 1 : 0;
+    return 0;
+}
+
 int pyotf_b200_hanser_info(const pyotf_hanser_t* h, int* K, int* rows, int* f0, int* nvec) {
     PYOTF_REQUIRE(h, "hanser_info: null handle");
     if (K) *K = h->K;

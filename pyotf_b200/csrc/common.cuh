@@ -58,6 +58,7 @@ struct pyotf_hanser {
     int* octij = nullptr;
     void* dtab = nullptr;           // [planes][dtab_size] per-plane defocus tables (scratch, grown on demand)
     size_t dtab_cap = 0;            // capacity of dtab in bytes
+    int overlap = 0;                // streaming mode (pyotf_b200_hanser_set_overlap)
 };
 
 struct pyotf_comm;

@@ -84,6 +84,14 @@ __device__ __forceinline__ double hypot_ref(double x, double y) {
     return h;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; it must call pdl_wait() before
+// touching anything the predecessor writes, and the predecessor lets it go with pdl_launch_dependents().
+// Both are no-ops for ordinary launches.  The PR loop and back-to-back K1 launches use them to overlap a kernel's launch
+// latency, prologue and (for K1) its whole compute phase with the tail of the previous kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int DIR, typename T> __device__ __forceinline__ void fft2(cplx<T>& a, cplx<T>& b) {
     cplx<T> t = a - b; a = a + b; b = t;
 }

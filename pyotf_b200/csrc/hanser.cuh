@@ -139,6 +139,7 @@ template <typename T> struct HanserArgs {
     const cplx<T>* tw;        // [N] e^{+2 pi i k/N}
     const cplx<T>* dtab;      // [nz][dtab_size] per-plane defocus tables (TAB variants) or nullptr
     int amp_in_tab;           // the tables already hold amp * D (ideal pupil, scalar model)
+    int overlap;              // host-side: streaming mode, launch with programmatic stream serialization
     const double* octkz;      // octant lists for the in-kernel table builders (symmetric box) or nullptr
     const T* octamp;
     const int* octij;
@@ -359,6 +360,7 @@ template <typename T, int N, int M, int TABM, bool SYM>
 __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
     constexpr bool TAB = TABM != 0;
     static_assert(!SYM || TAB, "the symmetric path needs the (symmetric-box) table");
+    pdl_launch_dependents();          // a following K1 launch may start filling the SMs this grid leaves idle
     using RP = FftPlan<N>;
     using CP = FftPlan<M>;
     using SM = HanserSmem<N, M, T>;
@@ -448,6 +450,9 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
         }
         __syncthreads();
         // ---------------- rows: FFT_N over kx + epilogue ----------------
+        // everything so far read per-handle constants and wrote shared memory only; the stores below must
+        // not overtake those of an earlier launch into the same buffers (no-op for ordinary launches)
+        if (v == 0) pdl_wait();
         {
             constexpr int R1 = RP::R1, L1 = RP::R2, G = RP::G, NG = SM::NG, PITCH = SM::PITCH;
             constexpr int CL1 = CP::R2, CQ1 = CP::R1;

@@ -87,6 +87,18 @@ int hanser_launch_nmt(const HanserArgs<T>& a, int batch, size_t smem, cudaStream
         attr[0].val.clusterDim.x = N / M; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         PYOTF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
+    } else if (TABM == 3 && a.pupilc == nullptr && a.overlap) {
+        // streaming mode (pyotf_b200_hanser_set_overlap): the caller promises that nothing this launch reads
+        // (z_dev; the handle's tables are immutable) is written by the kernel that precedes it in the stream, so
+        // back-to-back launches overlap (programmatic dependent launch; the kernel still waits for its
+        // predecessor right before its first global store, so output order is preserved)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(SM::NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        PYOTF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
     } else {
         kern<<<grid, SM::NT, smem, s>>>(a);
     }
@@ -221,6 +233,7 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
     a.kzc = h->kzc; a.ampc = (const T*)h->ampc; a.pupilc = (const cplx<T>*)pupilc;
     a.tw = (const cplx<T>*)h->tw; a.z = z; a.psfi = (T*)psfi; a.psfa = (cplx<T>*)psfa;
     a.K = h->K; a.KR = h->KR; a.KP = h->KP; a.f0 = h->f0; a.nz = nz; a.nvec = h->nvec; a.pupil_stride = pupil_stride;
+    a.overlap = h->overlap;
     int smem_limit = 0;
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     a.dtab = nullptr; a.amp_in_tab = 0;

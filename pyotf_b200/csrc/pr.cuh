@@ -28,14 +28,6 @@ struct PrState {
     int pad;
 };
 
-// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
-// attribute may start while its predecessor in the stream is still running; it must call pdl_wait() before
-// touching anything the predecessor writes, and the predecessor lets it go with pdl_launch_dependents().
-// Both are no-ops for ordinary launches.  The PR loop uses them to overlap each kernel's launch latency and
-// prologue (twiddles, defocus-table staging) with the tail of the previous kernel.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 template <typename T> struct PrPlaneArgs {
     const double* kzc;          // [KR][K]
     const cplx<T>* pupilc;      // [KR][K] current pupil (compact, zero padded rows)

@@ -112,3 +112,30 @@ def test_geometry_tables_match_oracle():
         theta = np.arcsin((kr < kmag) * kr / kmag)
         a = (1 / np.sqrt(np.cos(theta))) * (kr <= na / wl)
         np.testing.assert_allclose(amp[0], a[sub], rtol=1e-14)
+
+
+def test_streaming_mode_is_bit_identical():
+    """pyotf_b200_hanser_set_overlap: back-to-back launches overlap (programmatic dependent launch) but every
+    stack, including repeated launches into one buffer, equals the ordinary launch bit for bit."""
+    import torch
+
+    from pyotf_b200 import _engine as eng
+
+    h = eng.hanser_handle(520, 0.85, 1.0, 130, 256, "none", "sine", "fp32", -1)
+    zs = [eng.to_device_f64((np.arange(40) - 20 + 3 * k) * 300.0) for k in range(6)]
+    ref = [h.psf(z)[1].clone() for z in zs]
+    torch.cuda.synchronize()
+    h.set_overlap(True)
+    try:
+        outs = [torch.empty_like(ref[0]) for _ in zs]
+        same = torch.empty_like(ref[0])
+        for k, z in enumerate(zs):
+            h.psf(z, psfi_out=outs[k])
+        for z in zs:                       # six launches into ONE buffer: the last one must win everywhere
+            h.psf(z, psfi_out=same)
+        torch.cuda.synchronize()
+    finally:
+        h.set_overlap(False)
+    for k in range(6):
+        assert torch.equal(outs[k], ref[k]), k
+    assert torch.equal(same, ref[-1])
