@@ -262,6 +262,19 @@ __device__ __forceinline__ void hanser_build_dtab_cluster(cplx<T>* Dq, const dou
     }
 }
 
+// copy one plane's defocus table from global to shared memory, all of a thread's loads in flight at once
+template <typename T, int NT>
+__device__ __forceinline__ void stage_dtab(cplx<T>* __restrict__ dst, const cplx<T>* __restrict__ src, int n, int tid) {
+    constexpr int UNR = 8;
+    for (int i0 = tid; i0 < n; i0 += UNR * NT) {
+        cplx<T> v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) { const int i = i0 + u * NT; v[u] = i < n ? src[i] : mk<T>(0, 0); }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) { const int i = i0 + u * NT; if (i < n) dst[i] = v[u]; }
+    }
+}
+
 // what multiplies the defocus factor in the fold
 enum FoldMode {
     FOLD_TAB_ONLY = 0,    // nothing: the table already holds amp * D      (ideal pupil, scalar model)
@@ -418,8 +431,7 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
                 __syncthreads();
             }
             if constexpr (TABM == 1) {
-                const cplx<T>* __restrict__ src = a.dtab + (size_t)plane * dtab_size(a.f0);
-                for (int i = tid; i < dtab_size(a.f0); i += NT) Dq[i] = src[i];
+                stage_dtab<T, NT>(Dq, a.dtab + (size_t)plane * dtab_size(a.f0), dtab_size(a.f0), tid);
                 __syncthreads();
             }
         }

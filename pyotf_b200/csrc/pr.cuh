@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
     const int plane = blockIdx.x / R;
     cplx<T>* Dq = EX;                                            // staged defocus table (aliases EX, disjoint phases)
     const cplx<T>* __restrict__ dsrc = TAB ? a.dtab + (size_t)plane * dtab_size(a.f0) : nullptr;
-    if constexpr (TAB) for (int i = tid; i < dtab_size(a.f0); i += NT) Dq[i] = dsrc[i];
+    if constexpr (TAB) stage_dtab<T, NT>(Dq, dsrc, dtab_size(a.f0), tid);
     const int K = a.K, KP = a.KP, f0 = a.f0;
     const double z = a.z[plane];
     const cplx<T>* __restrict__ pupil = a.pupilc;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
     // ---------------- forward columns: FFT_M over y' (transpose of the inverse stages) ----------------
     {
         constexpr int Q1 = CP::R1, L1 = CP::R2, JMAX = N / L1;
-        if constexpr (TAB) for (int i = tid; i < dtab_size(a.f0); i += NT) Dq[i] = dsrc[i];   // EX is free again
+        if constexpr (TAB) stage_dtab<T, NT>(Dq, dsrc, dtab_size(a.f0), tid);                  // EX is free again
         if constexpr (L1 > 1) {
             if (colactive) {
                 for (int c1 = rl; c1 < Q1; c1 += nrl) {
