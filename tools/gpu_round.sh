@@ -11,7 +11,11 @@ python tools/prof_cmd.py k1 pr > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
     python tools/prof_cmd.py k1 pr > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
-python tools/prof_cmd.py k1 pr > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'hanser_psf_kernel|pr_plane_kernel|pr_finalize' -c 6 -f \
-    -o gpurun_out/hot_$TAG python tools/prof_cmd.py k1 pr > gpurun_out/ncu_full_$TAG.log 2>&1
-echo "full capture rc=$?"
+python tools/prof_cmd.py k1 > gpurun_out/plain_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'hanser_psf_kernel' -s 1 -c 1 -f \
+    -o gpurun_out/k1_$TAG python tools/prof_cmd.py k1 > gpurun_out/ncu_full_$TAG.log 2>&1
+echo "K1 capture rc=$?"
+python tools/prof_cmd.py pr > gpurun_out/plain_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'pr_plane_kernel|pr_finalize' -s 2 -c 2 -f \
+    -o gpurun_out/pr_$TAG python tools/prof_cmd.py pr > gpurun_out/ncu_full_$TAG.log 2>&1
+echo "K2 capture rc=$?"
