@@ -45,18 +45,29 @@ __host__ __device__ constexpr int radix_at(int L, int s) {
     }
 }
 
-// one in-place stage over all TI lines of the tile: blocks of length LB, radix R
-template <int DIR, typename T, int L, int LB, int R>
+// Shared-memory layout of a tile: line t starts at t * fft_pitch(L); element e of a line sits at
+// fft_pad(e) = e + e/16 (power-of-two lengths).  With the pitch odd (mod 16 elements) the 16 lines of a
+// tile fall into 16 different bank groups for any fixed element index, and the +e/16 skew spreads the
+// stride-16 / stride-8 accesses of the late stages and of the digit-reversed read-out.  Without it 87 % of
+// the shared-memory wavefronts of these kernels were bank-conflict replays (profiles/README.md).
+template <bool POW2> __host__ __device__ __forceinline__ constexpr int fft_pad(int e) { return POW2 ? e + (e >> 4) : e; }
+template <bool POW2> __host__ __device__ __forceinline__ constexpr int fft_pitch(int L) {
+    return POW2 ? ((L + (L >> 4)) | 1) : L + 1;
+}
+
+// one in-place stage over all lines of the tile: blocks of length LB, radix R.  Consecutive threads take
+// the SAME butterfly of consecutive LINES (conflict-free: the pitch is odd), then the next butterfly.
+template <int DIR, typename T, int L, int LB, int R, int TI>
 __device__ __forceinline__ void smem_stage(cplx<T>* tile, int pitch, int nlines, const cplx<T>* tw) {
     constexpr int LS = LB / R;            // sub-block length after this stage
     constexpr int NB = L / R;             // butterflies per line
-    for (int w = threadIdx.x; w < nlines * NB; w += blockDim.x) {
-        int line = w / NB, t = w - line * NB;
-        int blk = t / LS, bp = t - blk * LS;
-        cplx<T>* p = tile + (size_t)line * pitch + blk * LB + bp;
+    auto butterfly = [&](int line, int t) {
+        const int blk = t / LS, bp = t - blk * LS;
+        cplx<T>* base = tile + (size_t)line * pitch;
+        const int e0 = blk * LB + bp;
         cplx<T> x[R];
 #pragma unroll
-        for (int a = 0; a < R; ++a) x[a] = p[LS * a];
+        for (int a = 0; a < R; ++a) x[a] = base[fft_pad<true>(e0 + LS * a)];
         fft_radix<DIR, R>(x);
 #pragma unroll
         for (int c = 0; c < R; ++c) {
@@ -64,8 +75,13 @@ __device__ __forceinline__ void smem_stage(cplx<T>* tile, int pitch, int nlines,
                 cplx<T> w0 = tw[(bp * c * (L / LB)) & (L - 1)];
                 x[c] = DIR > 0 ? cmul(x[c], w0) : cmulc(x[c], w0);
             }
-            p[LS * c] = x[c];
+            base[fft_pad<true>(e0 + LS * c)] = x[c];
         }
+    };
+    if (nlines == TI) {
+        for (int w = threadIdx.x; w < TI * NB; w += blockDim.x) butterfly(w % TI, w / TI);
+    } else {
+        for (int w = threadIdx.x; w < nlines * NB; w += blockDim.x) butterfly(w % nlines, w / nlines);
     }
 }
 
@@ -93,7 +109,7 @@ template <int DIR, typename TIN, typename T, int L, int TI, bool POW2>
 __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __restrict__ src, cplx<T>* __restrict__ dst) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Lr = POW2 ? L : p.L;
-    const int pitch = Lr + 1;
+    const int pitch = fft_pitch<POW2>(Lr);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);        // [Lr]  e^{+2 pi i k / L}
     cplx<T>* tile = tw + Lr;                                    // [TI][pitch]
     cplx<T>* tile2 = tile + (size_t)TI * pitch;                 // DFT output (non-pow2 only)
@@ -158,7 +174,7 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
                     const int w = threadIdx.x + 256 * k;
                     const int t = w / L, l = w % L;
                     int i = l - p.in_shift; if (i < 0) i += L;
-                    tile[(size_t)t * pitch + i] = v[k];
+                    tile[(size_t)t * pitch + fft_pad<POW2>(i)] = v[k];
                 }
             } else {
 #pragma unroll
@@ -172,7 +188,7 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
                     const int w = threadIdx.x + 256 * k;
                     const int l = w / TI, t = w % TI;
                     int i = l - p.in_shift; if (i < 0) i += L;
-                    tile[(size_t)t * pitch + i] = v[k];
+                    tile[(size_t)t * pitch + fft_pad<POW2>(i)] = v[k];
                 }
             }
         }
@@ -182,13 +198,13 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int t = w / Lr, l = w - t * Lr;
             int i = l - p.in_shift; if (i < 0) i += Lr;       // src index l lands at x_in[i]
-            tile[(size_t)t * pitch + i] = load_as_cplx<TIN, T>(src, base + t * stride_t + l);
+            tile[(size_t)t * pitch + fft_pad<POW2>(i)] = load_as_cplx<TIN, T>(src, base + t * stride_t + l);
         }
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int l = w / nlines, t = w - l * nlines;
             int i = l - p.in_shift; if (i < 0) i += Lr;
-            tile[(size_t)t * pitch + i] = load_as_cplx<TIN, T>(src, base + t * stride_t + l * stride_l);
+            tile[(size_t)t * pitch + fft_pad<POW2>(i)] = load_as_cplx<TIN, T>(src, base + t * stride_t + l * stride_l);
         }
     }
     __syncthreads();
@@ -196,9 +212,9 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
     const T scale = (T)p.scale;
     if constexpr (POW2) {
         constexpr int r0 = radix_at(L, 0), r1 = radix_at(L, 1), r2 = radix_at(L, 2), ns = radix_count(L);
-        smem_stage<DIR, T, L, L, r0>(tile, pitch, nlines, tw);
-        if constexpr (ns > 1) { __syncthreads(); smem_stage<DIR, T, L, L / r0, r1>(tile, pitch, nlines, tw); }
-        if constexpr (ns > 2) { __syncthreads(); smem_stage<DIR, T, L, L / r0 / r1, r2>(tile, pitch, nlines, tw); }
+        smem_stage<DIR, T, L, L, r0, TI>(tile, pitch, nlines, tw);
+        if constexpr (ns > 1) { __syncthreads(); smem_stage<DIR, T, L, L / r0, r1, TI>(tile, pitch, nlines, tw); }
+        if constexpr (ns > 2) { __syncthreads(); smem_stage<DIR, T, L, L / r0 / r1, r2, TI>(tile, pitch, nlines, tw); }
         __syncthreads();
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
@@ -226,7 +242,7 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
                 const int t = contiguous ? w / L : w % TI, l = contiguous ? w % L : w / TI;
                 int o = l - p.out_shift; if (o < 0) o += L;
                 const int pos = digit_reversed_pos<L>(o);
-                dst[base + t * stride_t + l * stride_l] = cscale(res[(size_t)t * pitch + pos], scale);
+                dst[base + t * stride_t + l * stride_l] = cscale(res[(size_t)t * pitch + fft_pad<POW2>(pos)], scale);
             }
             return;
         }
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
             int o = l - p.out_shift; if (o < 0) o += Lr;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            dst[base + t * stride_t + l] = cscale(res[(size_t)t * pitch + pos], scale);
+            dst[base + t * stride_t + l] = cscale(res[(size_t)t * pitch + fft_pad<POW2>(pos)], scale);
         }
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
             int o = l - p.out_shift; if (o < 0) o += Lr;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            dst[base + t * stride_t + l * stride_l] = cscale(res[(size_t)t * pitch + pos], scale);
+            dst[base + t * stride_t + l * stride_l] = cscale(res[(size_t)t * pitch + fft_pad<POW2>(pos)], scale);
         }
     }
 }

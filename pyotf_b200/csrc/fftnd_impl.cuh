@@ -28,7 +28,7 @@ int fft_axis_launch_l(const AxisPass& p, const void* src, void* dst, int smem_li
     // lines per tile: 16 keeps 128 B (fp32) / 256 B (fp64) global segments on strided axes;
     // long axes drop to 8 / 4 lines so the tile still fits (and two CTAs share an SM when possible)
     const int Lr = POW2 ? L : p.L;
-    auto need = [&](int ti) { return sizeof(cplx<T>) * ((size_t)Lr + (size_t)ti * (Lr + 1) * (POW2 ? 1 : 2)); };
+    auto need = [&](int ti) { return sizeof(cplx<T>) * ((size_t)Lr + (size_t)ti * fft_pitch<POW2>(Lr) * (POW2 ? 1 : 2)); };
     const size_t soft = (size_t)smem_limit / 2 - 1024;
     if (need(16) <= soft || (need(8) > (size_t)smem_limit && need(16) <= (size_t)smem_limit))
         return fft_axis_launch_ti<DIR, TIN, T, L, POW2, 16>(p, src, dst, need(16), s);

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nline
     if (f.skip()) return;                                     // e.g. phase retrieval already converged
     typename F::Acc acc = F::acc_init();                      // per-thread accumulator of the store functor
     const int Lr = POW2 ? L : Lrt;
-    const int pitch = Lr + 1;
+    const int pitch = fft_pitch<POW2>(Lr);
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* tile = tw + Lr;
     cplx<T>* tile2 = tile + (size_t)TI * pitch;
@@ -52,25 +52,25 @@ __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nline
     if (LINE_MAJOR) {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int t = w / Lr, l = w - t * Lr;
-            tile[(size_t)t * pitch + l] = f.load(sline[t], l);
+            tile[(size_t)t * pitch + fft_pad<POW2>(l)] = f.load(sline[t], l);
         }
     } else if (nlines == TI) {                       // full tile: compile-time divisor
         for (int w = threadIdx.x; w < TI * Lr; w += blockDim.x) {
             int l = w / TI, t = w - l * TI;
-            tile[(size_t)t * pitch + l] = f.load(sline[t], l);
+            tile[(size_t)t * pitch + fft_pad<POW2>(l)] = f.load(sline[t], l);
         }
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int l = w / nlines, t = w - l * nlines;
-            tile[(size_t)t * pitch + l] = f.load(sline[t], l);
+            tile[(size_t)t * pitch + fft_pad<POW2>(l)] = f.load(sline[t], l);
         }
     }
     __syncthreads();
     if constexpr (POW2) {
         constexpr int r0 = radix_at(L, 0), r1 = radix_at(L, 1), r2 = radix_at(L, 2), ns = radix_count(L);
-        smem_stage<DIR, T, L, L, r0>(tile, pitch, nlines, tw);
-        if constexpr (ns > 1) { __syncthreads(); smem_stage<DIR, T, L, L / r0, r1>(tile, pitch, nlines, tw); }
-        if constexpr (ns > 2) { __syncthreads(); smem_stage<DIR, T, L, L / r0 / r1, r2>(tile, pitch, nlines, tw); }
+        smem_stage<DIR, T, L, L, r0, TI>(tile, pitch, nlines, tw);
+        if constexpr (ns > 1) { __syncthreads(); smem_stage<DIR, T, L, L / r0, r1, TI>(tile, pitch, nlines, tw); }
+        if constexpr (ns > 2) { __syncthreads(); smem_stage<DIR, T, L, L / r0 / r1, r2, TI>(tile, pitch, nlines, tw); }
         __syncthreads();
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
@@ -93,21 +93,21 @@ __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nline
             int t = w / Lr, o = w - t * Lr;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            f.store(sline[t], o, res[(size_t)t * pitch + pos], acc);
+            f.store(sline[t], o, res[(size_t)t * pitch + fft_pad<POW2>(pos)], acc);
         }
     } else if (nlines == TI) {
         for (int w = threadIdx.x; w < TI * Lr; w += blockDim.x) {
             int o = w / TI, t = w - o * TI;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            f.store(sline[t], o, res[(size_t)t * pitch + pos], acc);
+            f.store(sline[t], o, res[(size_t)t * pitch + fft_pad<POW2>(pos)], acc);
         }
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int o = w / nlines, t = w - o * nlines;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            f.store(sline[t], o, res[(size_t)t * pitch + pos], acc);
+            f.store(sline[t], o, res[(size_t)t * pitch + fft_pad<POW2>(pos)], acc);
         }
     }
     f.finish(acc);

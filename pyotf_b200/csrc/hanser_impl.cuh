@@ -173,7 +173,7 @@ int fft_lines_launch_ti(int Lr, long long nlines, F f, size_t smem, cudaStream_t
 
 template <int DIR, typename T, int L, bool POW2, bool LM, class F>
 int fft_lines_launch_l(int Lr, long long nlines, F f, int smem_limit, cudaStream_t s, int* nblocks_out) {
-    auto need = [&](int ti) { return sizeof(cplx<T>) * ((size_t)Lr + (size_t)ti * (Lr + 1) * (POW2 ? 1 : 2)); };
+    auto need = [&](int ti) { return sizeof(cplx<T>) * ((size_t)Lr + (size_t)ti * fft_pitch<POW2>(Lr) * (POW2 ? 1 : 2)); };
     const size_t soft = (size_t)smem_limit / 2 - 1024;
     if (need(16) <= soft || (need(8) > (size_t)smem_limit && need(16) <= (size_t)smem_limit))
         return fft_lines_launch_ti<DIR, T, L, POW2, LM, 16>(Lr, nlines, f, need(16), s, nblocks_out);
