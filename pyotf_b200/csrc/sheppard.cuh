@@ -40,7 +40,10 @@ __global__ void __launch_bounds__(256) sheppard_otf_kernel(SheppardParams p, cpl
     const double kx = fftfreq_at(x, p.N, p.kstep);
     const size_t plane = (size_t)p.N * p.N, vol = plane * p.NZ;
     // fftshift: index i moves to (i + n//2) mod n
-    const int xs = (x + p.N / 2) % p.N, ys = (y + p.N / 2) % p.N, zs = (zi + p.NZ / 2) % p.NZ;
+    int xs = x + p.N / 2, ys = y + p.N / 2, zs = zi + p.NZ / 2;
+    if (xs >= p.N) xs -= p.N;
+    if (ys >= p.N) ys -= p.N;
+    if (zs >= p.NZ) zs -= p.NZ;
     const size_t o = (size_t)zs * plane + (size_t)ys * p.N + xs;
     // numpy.linalg.norm(axis=0): sqrt(add.reduce(x * x)) in array order (kz, ky, kx)
     const double kr2 = __dadd_rn(__dadd_rn(__dmul_rn(kz, kz), __dmul_rn(ky, ky)), __dmul_rn(kx, kx));
