@@ -109,9 +109,11 @@ int hanser_launch_nmt(const HanserArgs<T>& a, int batch, size_t smem, cudaStream
 template <typename T, int N, int M>
 int hanser_launch_nm(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int batch, cudaStream_t s) {
     size_t smem = HanserSmem<N, M, T>::bytes(a.KP);
+#ifdef PYOTF_ENABLE_CLUSTER_TABLE   // experiment kept for the record (measured slower): -DPYOTF_ENABLE_CLUSTER_TABLE
     if (tabm == 2) {
         if constexpr (N / M <= 8) return hanser_launch_nmt<T, N, M, 2>(a, batch, smem, s);
     }
+#endif
     // ideal pupil of the scalar model: the even-symmetric variant (half the columns, half the rows)
     static const bool no_sym = getenv("PYOTF_B200_K1_NOSYM") != nullptr;
     const bool sym = a.amp_in_tab && !no_sym;
@@ -121,7 +123,7 @@ int hanser_launch_nm(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, in
 }
 
 template <typename T, int N> size_t hanser_smem_for(int M, int KP) {
-    if (M == 16) return HanserSmem<N, 16, T>::bytes(KP);
+    if (M == 16) return N <= 64 ? HanserSmem<N, 16, T>::bytes(KP) : (size_t)-1;
     if (M == 32) return HanserSmem<N, (N >= 32 ? 32 : 16), T>::bytes(KP);
     return HanserSmem<N, (N >= 64 ? 64 : 16), T>::bytes(KP);
 }
@@ -134,13 +136,13 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int
     int pick = 0;
     const int cand[3] = {64, 32, 16};
     static const int forced = [] { const char* e = getenv("PYOTF_B200_K1_ROWS"); return e ? atoi(e) : 0; }();   // tuning knob
-    if (forced && forced <= N && hanser_smem_for<T, N>(forced, a.KP) <= (size_t)smem_limit) pick = forced;
+    if (forced && forced <= N && (forced != 16 || N <= 64) && hanser_smem_for<T, N>(forced, a.KP) <= (size_t)smem_limit) pick = forced;
     // 64 or 32 rows per CTA, two CTAs per SM if the working set allows, else one; 16 rows only as a last
     // resort (its radix-16 fold spills registers badly: measured 20x slower)
     for (int pass = 0; pass < 3 && !pick; ++pass)
         for (int i = 0; i < 3 && !pick; ++i) {
             int M = cand[i];
-            if (M > N || (pass < 2 && M == 16 && N > 16)) continue;
+            if (M > N || (M == 16 && (pass < 2 || N > 64))) continue;   // 16 rows: small planes only, last resort
             size_t need = hanser_smem_for<T, N>(M, a.KP);
             size_t lim = pass == 0 ? (size_t)(smem_limit / 2 - 1024) : (size_t)smem_limit;
             if (need <= lim) pick = M;
@@ -149,7 +151,9 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int
     if (m_out) { *m_out = pick; return 0; }
     if (pick == 64) { if constexpr (N >= 64) return hanser_launch_nm<T, N, 64>(h, a, tabm, batch, s); }
     if (pick == 32) { if constexpr (N >= 32) return hanser_launch_nm<T, N, 32>(h, a, tabm, batch, s); }
-    return hanser_launch_nm<T, N, 16>(h, a, tabm, batch, s);
+    if constexpr (N <= 64) return hanser_launch_nm<T, N, 16>(h, a, tabm, batch, s);
+    set_error("hanser_psf: internal error (rows per CTA)");
+    return 1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -252,7 +256,12 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
         }
         if (rc) return rc;
         static const int k1_tab = [] { const char* e = getenv("PYOTF_B200_K1_TABLE"); return e ? atoi(e) : 0; }();
-        if (batch == 1 && k1_tab == 2 && h->N / M <= 8) {
+#ifdef PYOTF_ENABLE_CLUSTER_TABLE
+        const bool cluster_tab = batch == 1 && k1_tab == 2 && h->N / M <= 8;
+#else
+        const bool cluster_tab = false;
+#endif
+        if (cluster_tab) {
             tabm = 2;       // experiment: the plane's CTA cluster builds the table through DSMEM (measured slower)
         } else if (batch == 1 && k1_tab != 1) {
             tabm = 3;       // one stack: every CTA builds its own table (no separate launch)

@@ -23,7 +23,8 @@ template <typename T> int pr_pick_rows(const pyotf_hanser* h, int nz, int smem_l
     const int cand[3] = {64, 32, 16};
     if (want) {
         for (int i = 0; i < 3; ++i)
-            if (cand[i] == want && want <= h->N && pr_smem_for<T>(h->N, want, h->KP) <= (size_t)smem_limit) return want;
+            if (cand[i] == want && want <= h->N && (want != 16 || h->N <= 64) &&
+                pr_smem_for<T>(h->N, want, h->KP) <= (size_t)smem_limit) return want;
         return 0;
     }
     int pick = 0;
@@ -31,7 +32,7 @@ template <typename T> int pr_pick_rows(const pyotf_hanser* h, int nz, int smem_l
     for (int pass = 0; pass < 3 && !pick; ++pass)
         for (int i = 0; i < 3 && !pick; ++i) {
             int M = cand[i];
-            if (M > h->N || (pass < 2 && M == 16 && h->N > 16)) continue;
+            if (M > h->N || (M == 16 && (pass < 2 || h->N > 64))) continue;
             size_t lim = pass == 0 ? (size_t)(smem_limit / 2 - 1024) : (size_t)smem_limit;
             if (pr_smem_for<T>(h->N, M, h->KP) <= lim) pick = M;
         }
@@ -82,7 +83,9 @@ int pr_plane_launch_nm(const pyotf_hanser* h, int nth, const PrPlaneArgs<T>& a, 
 template <typename T, int N> int pr_plane_launch_n(const pyotf_hanser* h, int M, int nth, const PrPlaneArgs<T>& a, cudaStream_t s) {
     if (M == 64) { if constexpr (N >= 64) return pr_plane_launch_nm<T, N, 64>(h, nth, a, s); }
     if (M == 32) { if constexpr (N >= 32) return pr_plane_launch_nm<T, N, 32>(h, nth, a, s); }
-    return pr_plane_launch_nm<T, N, 16>(h, nth, a, s);
+    if constexpr (N <= 64) return pr_plane_launch_nm<T, N, 16>(h, nth, a, s);
+    set_error("pr: internal error (rows per CTA)");
+    return 1;
 }
 
 template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, bool pdl, cudaStream_t st) {
