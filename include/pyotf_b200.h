@@ -104,6 +104,11 @@ int pyotf_b200_hanser_defocus(const double* kz_dev, long long npix, const double
 /* out[mode][pt] = Z_{n[mode]}^{m[mode]}(r[pt], theta[pt]), float64; zero for r > 1. */
 int pyotf_b200_zernike(const double* r_dev, const double* theta_dev, long long npts, const int* n_dev,
                        const int* m_dev, int nmodes, int norm, double* out_dev, void* stream);
+/* Normal equations of the Zernike least-squares fit (phaseretrieval._fit_to_zerns, phaseretrieval.py:406-432):
+ * G [nmodes][nmodes + nrhs] = Z [Z^T | b^T] with Z [nmodes][npts] (pyotf_b200_zernike on the in-pupil pixels) and
+ * b [nrhs][npts] the data vectors; all float64 on the device.  The nmodes x nmodes solve stays on the host. */
+int pyotf_b200_zernike_gram(const double* z_dev, const double* b_dev, long long npts, int nmodes, int nrhs,
+                            double* g_out_dev, void* stream);
 /* Batched aberrated pupils in the handle's compact layout / dtype:
  *   pupil_b = (sum_j mcoefs[b][j] Z_j + |ideal pupil|) * exp(i sum_j pcoefs[b][j] Z_j)
  * with Z_j evaluated at r = kr*wl/na, theta = phi (otf.py:626-642).  n_dev/m_dev are the

@@ -297,6 +297,30 @@ def zernike_eval(r, theta, n, m, norm):
     return out.cpu().numpy()
 
 
+def zernike_lstsq(r, theta, n, m, data):
+    """Least-squares coefficients of `data` rows ([nrhs, npts]) on the Zernike modes (n, m) evaluated at the points
+    (r, theta): modes and normal equations on the GPU (fp64), the nmodes x nmodes solve on the host.
+    Returns [nrhs, nmodes]."""
+    torch = _torch()
+    rd, td = to_device_f64(np.ravel(r)), to_device_f64(np.ravel(theta))
+    nd, md = to_device_i32(n), to_device_i32(m)
+    b = to_device_f64(np.atleast_2d(data))
+    npts, nmodes, nrhs = rd.numel(), nd.numel(), b.shape[0]
+    Z = torch.empty((nmodes, npts), dtype=torch.float64, device="cuda")
+    lib = _lib.load()
+    _lib.check(lib.pyotf_b200_zernike(ptr(rd), ptr(td), npts, ptr(nd), ptr(md), nmodes, 1, ptr(Z), stream_ptr()))
+    G = torch.empty((nmodes, nmodes + nrhs), dtype=torch.float64, device="cuda")
+    _lib.check(lib.pyotf_b200_zernike_gram(ptr(Z), ptr(b), npts, nmodes, nrhs, ptr(G), stream_ptr()))
+    g = G.cpu().numpy()
+    A, rhs = g[:, :nmodes], g[:, nmodes:]
+    A = 0.5 * (A + A.T)
+    try:
+        coefs = np.linalg.solve(A, rhs)
+    except np.linalg.LinAlgError:       # rank deficient (e.g. more modes than pixels): minimum-norm solution
+        coefs = np.linalg.lstsq(A, rhs, rcond=None)[0]
+    return coefs.T
+
+
 def hanser_kspace(wl, ni, res, size):
     """(kr, phi, kz) float64 [N, N] device tensors, unshifted (HanserPSF._gen_kr)."""
     torch = _torch()

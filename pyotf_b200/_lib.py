@@ -50,6 +50,7 @@ PROTOTYPES = {
     "pyotf_b200_hanser_kspace": (_i, [_d, _d, _d, _i, _vp, _vp, _vp, _vp]),
     "pyotf_b200_hanser_defocus": (_i, [_vp, _ll, _vp, _i, _vp, _vp]),
     "pyotf_b200_zernike": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _vp, _vp]),
+    "pyotf_b200_zernike_gram": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
     "pyotf_b200_fftn": (_i, [_vp, _vp, _i, C.POINTER(_ll), _ip, _i, _i, _i, _i, _i, _i, _vp]),
     "pyotf_b200_abs2_sum0": (_i, [_vp, _i, _ll, _vp, _i, _vp]),
     "pyotf_b200_hanser_aberration_pupil": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),

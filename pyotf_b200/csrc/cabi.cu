@@ -217,6 +217,15 @@ int pyotf_b200_zernike(const double* r, const double* theta, long long npts, con
     return 0;
 }
 
+int pyotf_b200_zernike_gram(const double* Z, const double* b, long long npts, int nmodes, int nrhs, double* G, void* stream) {
+    PYOTF_REQUIRE(Z && G && npts > 0 && nmodes > 0 && nrhs >= 0 && (nrhs == 0 || b), "zernike_gram: bad argument");
+    PYOTF_REQUIRE(nmodes <= 65535 && nmodes + nrhs <= 65535, "zernike_gram: too many modes");
+    dim3 grid((unsigned)(nmodes + nrhs), (unsigned)nmodes);
+    zernike_gram_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Z, b, npts, nmodes, nrhs, G);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int pyotf_b200_hanser_aberration_pupil(const pyotf_hanser_t* h, const int* n, const int* m, int nmodes,
                                        const double* mc, const double* pc, int batch, void* out, void* stream) {
     PYOTF_REQUIRE(h && n && m && out, "aberration_pupil: null argument");

@@ -56,6 +56,25 @@ static __global__ void zernike_eval_kernel(const double* __restrict__ r, const d
     for (int j = 0; j < nmodes; ++j) out[(size_t)j * npts + p] = zernike_value(rr, th, n[j], m[j], norm);
 }
 
+// Normal equations of the Zernike least-squares fit (phaseretrieval._fit_to_zerns, pyotf/phaseretrieval.py:406-432):
+// G[i][j] = sum_p Z_i(p) Z_j(p), rhs[k][i] = sum_p Z_i(p) b_k(p) over the npts in-pupil pixels.  Z [nmodes][npts] is
+// the output of zernike_eval_kernel, b [nrhs][npts] the data vectors (magnitude, phase).  One CTA per (i, j) with
+// j <= nmodes + nrhs - 1: columns j >= nmodes are the right-hand sides.  fp64, fixed-order reduction.
+static __global__ void __launch_bounds__(128) zernike_gram_kernel(const double* __restrict__ Z, const double* __restrict__ b,
+                                                                  long long npts, int nmodes, int nrhs,
+                                                                  double* __restrict__ G /* [nmodes][nmodes + nrhs] */) {
+    __shared__ double red[4];
+    const int i = blockIdx.y, j = blockIdx.x;
+    const double* __restrict__ u = Z + (size_t)i * npts;
+    const double* __restrict__ v = j < nmodes ? Z + (size_t)j * npts : b + (size_t)(j - nmodes) * npts;
+    double acc = 0.0;
+    for (long long p = threadIdx.x; p < npts; p += blockDim.x) acc += u[p] * v[p];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) G[(size_t)i * (nmodes + nrhs) + j] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
 struct AberrationParams {
     int N, K, KR, f0;
     int nmodes, batch;

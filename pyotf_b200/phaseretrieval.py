@@ -142,13 +142,18 @@ class PhaseRetrievalResult(object):
         return wavefront_flat.max() - wavefront_flat.min()
 
     def fit_to_zernikes(self, num_zerns, *, mapping=noll2degrees):
-        """Least-squares fit of mag and phase to the first ``num_zerns`` modes (pyotf/phaseretrieval.py:201-211)."""
+        """Least-squares fit of mag and phase to the first ``num_zerns`` modes (pyotf/phaseretrieval.py:201-211).
+
+        The modes are evaluated on the in-pupil pixels and the normal equations are accumulated on the GPU
+        (``pyotf_b200_zernike`` + ``pyotf_b200_zernike_gram``, fp64); only the num_zerns x num_zerns solve runs on
+        the host.  ``zd_result.zerns`` (the full-grid modes the reference stores eagerly) is evaluated on first use.
+        """
         r, theta = self.r, self.theta
         r = r / (self.na / self.wl)
-        zerns = zernike(r, theta, *mapping(np.arange(1, num_zerns + 1)))
-        mag_coefs = _fit_to_zerns(self.mag, zerns, r)
-        phase_coefs = _fit_to_zerns(self.phase, zerns, r)
-        self.zd_result = ZernikeDecomposition(mag_coefs, phase_coefs, zerns)
+        n, m = mapping(np.arange(1, num_zerns + 1))
+        valid = r <= 1
+        coefs = _engine.zernike_lstsq(r[valid], theta[valid], n, m, np.stack([self.mag[valid], self.phase[valid]]))
+        self.zd_result = ZernikeDecomposition(coefs[0], coefs[1], _LazyZerns(r, theta, n, m))
         return self.zd_result
 
     def _generate_psf(self, complex_pupil, size=None, zsize=None, zrange=None):
@@ -199,7 +204,18 @@ class ZernikeDecomposition(object):
         assert mag_coefs.size == phase_coefs.size == zerns.shape[0]
         self.mcoefs = mag_coefs
         self.pcoefs = phase_coefs
-        self.zerns = zerns
+        self._zerns = zerns
+
+    @property
+    def zerns(self):
+        """(m, N, N) Zernike modes used in the decomposition (evaluated on first access)."""
+        if isinstance(self._zerns, _LazyZerns):
+            self._zerns = self._zerns.evaluate()
+        return self._zerns
+
+    @zerns.setter
+    def zerns(self, value):
+        self._zerns = value
 
     @property
     def rms_error(self):
@@ -229,6 +245,17 @@ class ZernikeDecomposition(object):
 
     def plot(self, smag=slice(None), sphase=slice(None), axs=None):
         raise NotImplementedError("plotting is out of scope for pyotf_b200")
+
+
+class _LazyZerns:
+    """Full-grid Zernike modes, evaluated (on the GPU) only when somebody asks for them."""
+
+    def __init__(self, r, theta, n, m):
+        self.r, self.theta, self.n, self.m = r, theta, n, m
+        self.shape = (len(n),) + r.shape
+
+    def evaluate(self):
+        return zernike(self.r, self.theta, self.n, self.m)
 
 
 def _calc_mse(data1, data2):

@@ -251,3 +251,22 @@ def test_generic_size_path_vs_oracle(size, nz, precision):
                                  pupil_tol=3e-3, mse_tol=0)
     r2 = retrieve_phase(data, dict(params), 40, 3e-3, 0, precision=precision, rows_per_cta=1)
     assert len(r2.mse) == o2["iters"]
+
+
+def test_fit_to_zernikes_device_normal_equations_vs_host_lstsq():
+    """fit_to_zernikes: GPU normal equations + host solve against the reference's formulation
+    (numpy.linalg.lstsq on the full mode stack, phaseretrieval.py:406-432), 120 Noll modes at 256^2."""
+    from pyotf_b200.phaseretrieval import _fit_to_zerns, _recon_from_zerns, retrieve_phase
+    from pyotf_b200.zernike import noll2degrees, zernike
+
+    data = _fixture_data()
+    r = retrieve_phase(data, dict(OPT), 20, 0, 0, precision="fp64")
+    zd = r.fit_to_zernikes(120)
+    rr = r.r / (r.na / r.wl)
+    zerns = zernike(rr, r.theta, *noll2degrees(np.arange(1, 121)))
+    ref_m, ref_p = _fit_to_zerns(r.mag, zerns, rr), _fit_to_zerns(r.phase, zerns, rr)
+    assert rel_l2(zd.mcoefs, ref_m) <= 1e-9 and rel_l2(zd.pcoefs, ref_p) <= 1e-9
+    assert zd.zerns.shape == (120, 256, 256) and rel_l2(zd.zerns, zerns) == 0.0
+    assert rel_l2(zd.phase(slice(4, None)), _recon_from_zerns(ref_p[4:], zerns[4:])) <= 1e-9
+    assert zd.complex_pupil().shape == (256, 256) and np.isfinite(zd.rms_error)
+    assert r.generate_zd_psf().shape == (25, 256, 256)
