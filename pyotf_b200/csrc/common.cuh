@@ -41,6 +41,13 @@ inline void keep_scratch_pool() {
     done_for = dev;
 }
 
+constexpr int PYOTF_MAX_DEVICES = 64;
+inline int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < PYOTF_MAX_DEVICES ? dev : 0;
+}
+
 constexpr int PYOTF_PAD_ROWS = 64;   // >= the largest rows-per-CTA M of K1
 inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 

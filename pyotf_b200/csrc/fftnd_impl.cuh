@@ -11,10 +11,11 @@ namespace pyotf {
 template <int DIR, typename TIN, typename T, int L, bool POW2, int TI>
 int fft_axis_launch_ti(const AxisPass& p, const void* src, void* dst, size_t smem, cudaStream_t s) {
     auto kern = fft_axis_kernel<DIR, TIN, T, L, TI, POW2>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
+    static thread_local size_t configured[PYOTF_MAX_DEVICES] = {};      // the attribute is per device
+    const int dev_slot = current_device_slot();
+    if (smem > configured[dev_slot]) {
         PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[dev_slot] = smem;
     }
     long long nblocks = p.n_inner == 1 ? (p.n_outer + TI - 1) / TI : p.n_outer * ((p.n_inner + TI - 1) / TI);
     PYOTF_REQUIRE(nblocks > 0 && nblocks < (1ll << 31), "fft: bad grid");

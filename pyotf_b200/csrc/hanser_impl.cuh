@@ -73,10 +73,11 @@ template <typename T, int N, int M, int TABM, bool SYM = false>
 int hanser_launch_nmt(const HanserArgs<T>& a, int batch, size_t smem, cudaStream_t s) {
     using SM = HanserSmem<N, M, T>;
     auto kern = hanser_psf_kernel<T, N, M, TABM, SYM>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
+    static thread_local size_t configured[PYOTF_MAX_DEVICES] = {};      // the attribute is per device
+    const int dev_slot = current_device_slot();
+    if (smem > configured[dev_slot]) {
         PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[dev_slot] = smem;
     }
     dim3 grid((unsigned)((N / M) * a.nz), (unsigned)batch);
     if constexpr (TABM == 2) {
@@ -162,10 +163,11 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int
 template <int DIR, typename T, int L, bool POW2, bool LM, int TI, class F>
 int fft_lines_launch_ti(int Lr, long long nlines, F f, size_t smem, cudaStream_t s, int* nblocks_out) {
     auto kern = fft_lines_kernel<DIR, T, L, TI, POW2, LM, F>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
+    static thread_local size_t configured[PYOTF_MAX_DEVICES] = {};      // the attribute is per device
+    const int dev_slot = current_device_slot();
+    if (smem > configured[dev_slot]) {
         PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[dev_slot] = smem;
     }
     long long nblocks = (nlines + TI - 1) / TI;
     PYOTF_REQUIRE(nblocks > 0 && nblocks < (1ll << 31), "hanser_psf: bad grid");

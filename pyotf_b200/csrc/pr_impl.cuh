@@ -50,10 +50,11 @@ template <typename T, int N, int M, bool TAB, int NTH>
 int pr_plane_launch_nmt(const PrPlaneArgs<T>& a, cudaStream_t s) {
     const size_t smem = HanserSmem<N, M, T, NTH>::bytes(a.KP);
     auto kern = pr_plane_kernel<T, N, M, TAB, NTH>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
+    static thread_local size_t configured[PYOTF_MAX_DEVICES] = {};      // the attribute is per device
+    const int dev_slot = current_device_slot();
+    if (smem > configured[dev_slot]) {
         PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[dev_slot] = smem;
     }
     if (a.pdl) {
         cudaLaunchConfig_t cfg = {};
