@@ -481,10 +481,11 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         alg_bytes = nz * N * N * esize  # N^2 * s_r per plane -> PSFi only
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-                traffic = json.load(f).get(precision)
+                tj = json.load(f)
+            traffic, traffic_note = tj.get(precision), tj.get("_note")
         except Exception:
             pass
         line = {
@@ -500,7 +501,7 @@ def run_ours(args):
                                  f"launch stream, max over ranks",
                        "parallelism": f"z-shard x{world} (no collective)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "kernel": "hanser_psf_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "streaming_mode": {"ms_per_step": stream_ms, "planes_per_s": nz * world / (stream_ms * 1e-3),
                                             "achieved": alg_bytes / (stream_ms * 1e-3) / 1e9,
