@@ -122,7 +122,7 @@ int pyotf_b200_hanser_create(const pyotf_hanser_params* p, void* stream, pyotf_h
 
 int pyotf_b200_hanser_destroy(pyotf_hanser_t* h) {
     if (!h) return 0;
-    cudaFree(h->kzc); cudaFree(h->ampc); cudaFree(h->maskc); cudaFree(h->tw); cudaFree(h->dtab); cudaFree(h->octkz); cudaFree(h->octamp); cudaFree(h->octij);
+    cudaFree(h->kzc); cudaFree(h->ampc); cudaFree(h->maskc); cudaFree(h->tw); cudaFree(h->dtab); cudaFree(h->octkz); cudaFree(h->octamp); cudaFree(h->octij); cudaFree(h->pscratch);
     delete h;
     return 0;
 }

@@ -66,6 +66,8 @@ struct pyotf_hanser {
     void* dtab = nullptr;           // [planes][dtab_size] per-plane defocus tables (scratch, grown on demand)
     size_t dtab_cap = 0;            // capacity of dtab in bytes
     int overlap = 0;                // streaming mode (pyotf_b200_hanser_set_overlap)
+    void* pscratch = nullptr;       // pupil * amp of the last launch (scalar model), grown on demand
+    size_t pscratch_cap = 0;
 };
 
 struct pyotf_comm;

@@ -116,6 +116,16 @@ __global__ void pack_pupil_kernel(int N, int K, int KR, int f0, const double2* _
     dst[idx] = mk<T>((T)v.x, (T)v.y);
 }
 
+// pupil * amp for the scalar model, once per launch: every CTA of every plane then reads one table
+// instead of two in its fold (a library launch has 256 CTAs per entry re-reading them from L2)
+template <typename T>
+__global__ void pupil_premul_kernel(const cplx<T>* __restrict__ pupil, const T* __restrict__ amp, cplx<T>* __restrict__ out,
+                                    int KKP, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    out[i] = cscale(pupil[i], amp[(int)(i % KKP)]);
+}
+
 // bounding half-width (in frequency index) of the non-zero support of an unshifted N x N pupil
 static __global__ void pupil_support_kernel(int N, const double2* __restrict__ src, int* __restrict__ hmax) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,6 +150,7 @@ template <typename T> struct HanserArgs {
     const cplx<T>* dtab;      // [nz][dtab_size] per-plane defocus tables (TAB variants) or nullptr
     int amp_in_tab;           // the tables already hold amp * D (ideal pupil, scalar model)
     int overlap;              // host-side: streaming mode, launch with programmatic stream serialization
+    int pupil_has_amp;        // pupilc was pre-multiplied by the (single) apodisation table
     const double* octkz;      // octant lists for the in-kernel table builders (symmetric box) or nullptr
     const T* octamp;
     const int* octij;
@@ -442,7 +453,8 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
         {
             constexpr int Q1 = CP::R1, L1 = CP::R2;
             if (colactive) {
-                if (pupil) hanser_fold_cols<TAB, FOLD_PUPIL_AMP, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
+                if (pupil && a.pupil_has_amp) hanser_fold_cols<TAB, FOLD_PUPIL, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
+                else if (pupil) hanser_fold_cols<TAB, FOLD_PUPIL_AMP, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
                 else if (TAB && tab_only) hanser_fold_cols<TAB, TAB ? FOLD_TAB_ONLY : FOLD_AMP, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
                 else hanser_fold_cols<TAB, FOLD_AMP, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
             }

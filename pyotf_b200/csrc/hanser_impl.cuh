@@ -242,6 +242,28 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
     a.overlap = h->overlap;
     int smem_limit = 0;
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    a.pupil_has_amp = 0;
+    const bool fused_size = h->N == 32 || h->N == 64 || h->N == 128 || h->N == 256;
+    if (pupilc && h->nvec == 1 && fused_size) {
+        // scalar model: fold the apodisation into the pupil(s) once per launch (scratch owned by the handle;
+        // like the table scratch it makes a handle single-stream)
+        pyotf_hanser* hm = const_cast<pyotf_hanser*>(h);
+        const size_t KKP = (size_t)h->KR * h->K;
+        const long long total = (long long)KKP * (pupil_stride ? batch : 1);
+        const size_t need = (size_t)total * sizeof(cplx<T>);
+        if (need > hm->pscratch_cap) {
+            PYOTF_CUDA_OK(cudaStreamSynchronize(s));
+            cudaFree(hm->pscratch); hm->pscratch = nullptr; hm->pscratch_cap = 0;
+            PYOTF_CUDA_OK(cudaMalloc(&hm->pscratch, need));
+            hm->pscratch_cap = need;
+        }
+        PYOTF_REQUIRE(pupil_stride == 0 || pupil_stride == (long long)KKP, "hanser_psf: pupil_stride must be 0 or rows*K");
+        pupil_premul_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const cplx<T>*)pupilc, (const T*)h->ampc,
+                                                                              (cplx<T>*)hm->pscratch, (int)KKP, total);
+        PYOTF_CUDA_OK(cudaGetLastError());
+        a.pupilc = (const cplx<T>*)hm->pscratch;
+        a.pupil_has_amp = 1;
+    }
     a.dtab = nullptr; a.amp_in_tab = 0;
     a.octkz = h->octkz; a.octamp = (const T*)h->octamp; a.octij = h->octij;
     const int ntab = h->octkz ? hanser_ntab<T>(h) : 0;
