@@ -40,6 +40,17 @@ def main():
         st = eng.PRState(520, 0.85, 1.0, 130, 256, zall, torch.as_tensor(data.astype(dt), device="cuda"), precision)
         mse, _, _ = st.run(6, 0.0, 0.0)
         print("pr ok", mse[-1])
+    if "lib" in what:
+        from pyotf_b200.otf import HanserPSF, _aberrated_pupils
+
+        base = HanserPSF(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=256, zsize=64, precision=precision)
+        coefs = np.random.default_rng(0).standard_normal((32, 120)) * 0.1
+        z = eng.to_device_f64(base.zrange)
+        for _ in range(2):
+            pupils = _aberrated_pupils(base, None, coefs)
+            _, psfi = pupils.handle(base).psf(z, pupils.tensor, want_psfa=False, want_psfi=True)
+        torch.cuda.synchronize()
+        print("lib ok", float(psfi.sum()))
     if "big" in what:
         from pyotf_b200.otf import HanserPSF, _aberrated_pupils
 
