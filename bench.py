@@ -374,6 +374,7 @@ def run_ours(args):
     from pyotf_b200 import _lib
     from pyotf_b200.otf import HanserPSF
 
+    numa_node = eng.bind_to_gpu_numa_node(local) if world > 1 else None   # before any pinned allocation
     precision = args.precision
     rt = torch.float32 if precision == "fp32" else torch.float64
     esize = 4 if precision == "fp32" else 8
@@ -511,7 +512,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": nz * world / e2e_s, "unit": "planes/s", "h2d_bytes_per_step": int(zr.nbytes),
                     "d2h_bytes_per_step": int(nz * N * N * esize), "ms_per_step": 1e3 * e2e_s,
-                    "path": "HanserPSF.zrange = host array; HanserPSF.PSFi -> numpy (pinned D2H)"},
+                    "path": "HanserPSF.zrange = host array; HanserPSF.PSFi -> numpy (pinned D2H)",
+                    "numa_node_rank0": numa_node},
             # per step: one hanser_psf_kernel launch (4-CTA clusters build the defocus tables through DSMEM)
             "gpu_launches": args.steps,
         }

@@ -238,6 +238,37 @@ def nccl_library_path():
     return "libnccl.so.2"
 
 
+def bind_to_gpu_numa_node(device=None):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (one process per GPU).
+
+    Pinned staging buffers are then allocated on, and filled by, the memory controller next to the GPU's
+    PCIe root; with 8 ranks on a two-socket host this is what keeps the device-to-host copies of the
+    e2e path from crossing the socket interconnect.  Returns the node id, or None when the topology is
+    not exposed (VMs) -- in which case nothing is changed."""
+    torch = _torch()
+    try:
+        dev = torch.cuda.current_device() if device is None else int(device)
+        p = torch.cuda.get_device_properties(dev)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_bounds(n, rank, world):
     """Contiguous block [lo, hi) of n items owned by `rank` (np.array_split sizes)."""
     base, extra = divmod(int(n), int(world))
