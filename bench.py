@@ -234,6 +234,20 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100):
         t0 = time.perf_counter()
         r = retrieve_phase(data, dict(params), iters, 0, 0, precision=precision)
         dt_s = time.perf_counter() - t0
+        # the same from the raw camera stack (uint16): background removal / clip on the device (N3), then the loop
+        from pyotf_b200.utils import prep_data_for_PR, prep_data_for_PR_dev
+
+        raw = np.load(os.path.join(ROOT, "tests", "golden", "fixture_psf_520.npz"))["raw"]
+        retrieve_phase(prep_data_for_PR_dev(raw, 256, 1.1, precision=precision), dict(params), iters, 0, 0, precision=precision)
+        t0 = time.perf_counter()
+        retrieve_phase(prep_data_for_PR_dev(raw, 256, 1.1, precision=precision), dict(params), iters, 0, 0, precision=precision)
+        dt_raw = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        prep_data_for_PR(raw, 256, 1.1)
+        dt_prep_cpu = time.perf_counter() - t0
+        out["e2e_from_raw_u16"] = {"iters_per_s": iters / dt_raw, "ms_total": 1e3 * dt_raw, "h2d_bytes": int(raw.nbytes),
+                                   "host_prep_ms_for_comparison": 1e3 * dt_prep_cpu,
+                                   "path": "prep_data_for_PR_dev(uint16 stack) -> retrieve_phase(device tensor)"}
         out["e2e"] = {"iters_per_s": iters / dt_s, "ms_total": 1e3 * dt_s, "h2d_bytes": int(data.nbytes),
                       "d2h_bytes": int(r.pupil.nbytes + 3 * 8 * iters),
                       "path": "retrieve_phase(host ndarray) -> PhaseRetrievalResult incl. host unwrap"}

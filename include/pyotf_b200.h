@@ -146,6 +146,18 @@ int pyotf_b200_sheppard_psf(const pyotf_sheppard_params* params, void* otfa_out_
                             void* psfi_out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Data preparation for phase retrieval  (pyotf/utils.py:76-201)
+ * ---------------------------------------------------------------------------------- */
+/* prep_data_for_PR for an unsigned 16-bit camera stack on the device: mode-based background removal
+ * (remove_bg, utils.py:127-147), pad (xysize >= max(ny, nx)) or centre-on-maximum + crop (center_data,
+ * utils.py:76-124), clip at zero (utils.py:201).
+ *   data_u16_dev [nz][ny][nx];  xysize <= 0 means max(ny, nx);  out_dev [nz][xysize][xysize] in `dtype`
+ *   mode_host    receives the background mode (may be NULL).  SYNCHRONISES the stream (the crop branch
+ *   needs the arg-max on the host to lay out the gather). */
+int pyotf_b200_prep_data_u16(const unsigned short* data_u16_dev, int nz, int ny, int nx, int xysize, double multiplier,
+                             int dtype, void* out_dev, int* mode_host, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Phase retrieval  (pyotf/phaseretrieval.py:32-149, the loop :95-135, _calc_mse :401-403)
  * ---------------------------------------------------------------------------------- */
 typedef struct pyotf_pr pyotf_pr_t;

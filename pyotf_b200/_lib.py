@@ -56,6 +56,7 @@ PROTOTYPES = {
     "pyotf_b200_hanser_aberration_pupil": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "pyotf_b200_sheppard_otfa": (_i, [C.POINTER(SheppardParams), _vp, _vp, _vp]),
     "pyotf_b200_sheppard_psf": (_i, [C.POINTER(SheppardParams), _vp, _vp, _vp, _vp]),
+    "pyotf_b200_prep_data_u16": (_i, [_vp, _i, _i, _i, _i, _d, _i, _vp, _ip, _vp]),
     "pyotf_b200_pr_create": (_i, [C.POINTER(HanserParams), _vp, _i, _ll, _vp, _i, _i, _vp, C.POINTER(_vp)]),
     "pyotf_b200_pr_destroy": (_i, [_vp]),
     "pyotf_b200_pr_info": (_i, [_vp, _ip, _ip, _ip, _ip, _ip]),

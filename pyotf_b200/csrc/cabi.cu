@@ -3,6 +3,7 @@
 #include "hanser.cuh"
 #include "zernike.cuh"
 #include "sheppard.cuh"
+#include "prep.cuh"
 
 namespace pyotf {
 static thread_local std::string g_last_error;
@@ -213,6 +214,52 @@ int pyotf_b200_zernike(const double* r, const double* theta, long long npts, con
     PYOTF_REQUIRE(r && theta && n && m && out && npts > 0 && nmodes > 0, "zernike: bad argument");
     zernike_eval_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, (cudaStream_t)stream>>>(r, theta, npts, n, m, nmodes,
                                                                                          norm, out);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pyotf_b200_prep_data_u16(const unsigned short* data, int nz, int ny, int nx, int xysize, double multiplier, int dtype,
+                             void* out, int* mode_host, void* stream) {
+    PYOTF_REQUIRE(data && out && nz > 0 && ny > 0 && nx > 0, "prep_data_u16: bad argument");
+    PYOTF_REQUIRE(dtype == PYOTF_F32 || dtype == PYOTF_F64, "prep_data_u16: bad dtype");
+    if (xysize <= 0) xysize = ny > nx ? ny : nx;                                  // utils.py:186-187
+    cudaStream_t s = (cudaStream_t)stream;
+    keep_scratch_pool();
+    const long long n = (long long)nz * ny * nx;
+    unsigned int* hist = nullptr;        // 65536 counts | argmax key (2 words) | mode
+    PYOTF_CUDA_OK(cudaMallocAsync(&hist, (65536 + 4) * sizeof(unsigned int), s));
+    PYOTF_CUDA_OK(cudaMemsetAsync(hist, 0, (65536 + 4) * sizeof(unsigned int), s));
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(hist + 65536);
+    int* mode_dev = reinterpret_cast<int*>(hist + 65536 + 2);
+    const int nb = (int)((n + 256 * 8 - 1) / (256 * 8));
+    prep_hist_kernel<<<nb < 1 ? 1 : (nb > 2368 ? 2368 : nb), 256, 0, s>>>(data, n, hist, key);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    prep_mode_kernel<<<1, 1024, 0, s>>>(hist, mode_dev);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    struct { unsigned long long key; int mode; int pad; } h;
+    PYOTF_CUDA_OK(cudaMemcpyAsync(&h, key, 16, cudaMemcpyDeviceToHost, s));
+    PYOTF_CUDA_OK(cudaStreamSynchronize(s));
+    PYOTF_CUDA_OK(cudaFreeAsync(hist, s));
+    if (mode_host) *mode_host = h.mode;
+    PrepGeom g = {};
+    g.nz = nz; g.ny = ny; g.nx = nx; g.oy = g.ox = xysize;
+    if (xysize == ny && xysize == nx) g.mode = 0;                                  // utils.py:190-191
+    else if (xysize >= (ny > nx ? ny : nx)) {                                      // fft_pad   utils.py:192-194
+        g.mode = 1; g.by = xysize / 2 - ny / 2; g.bx = xysize / 2 - nx / 2;
+    } else {                                                                       // centre + crop  utils.py:195-199
+        g.mode = 2;
+        const long long flat = (long long)(0xFFFFFFFFFFull - (h.key & 0xFFFFFFFFFFull));
+        const int pz = (int)(flat / ((long long)ny * nx)), py = (int)((flat / nx) % ny), px = (int)(flat % nx);
+        g.sz = nz / 2 - pz; g.sy = ny / 2 - py; g.sx = nx / 2 - px;                 // center_data  utils.py:119-123
+        // slice_maker(((ny + 1) // 2, (nx + 1) // 2), xysize): start = centre - width // 2, clipped at 0
+        g.y0 = (ny + 1) / 2 - xysize / 2; if (g.y0 < 0) g.y0 = 0;
+        g.x0 = (nx + 1) / 2 - xysize / 2; if (g.x0 < 0) g.x0 = 0;
+    }
+    const double bg = multiplier * (double)h.mode;
+    const long long total = (long long)nz * xysize * xysize;
+    const unsigned nblk = (unsigned)((total + 255) / 256);
+    if (dtype == PYOTF_F32) prep_gather_kernel<float><<<nblk, 256, 0, s>>>(g, data, bg, (float*)out);
+    else prep_gather_kernel<double><<<nblk, 256, 0, s>>>(g, data, bg, (double*)out);
     PYOTF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -125,6 +125,37 @@ def fft_pad(data, newshape, mode="constant"):
     return np.pad(data, pads, mode=mode)
 
 
+def prep_data_for_PR_dev(data, xysize=None, multiplier=1.05, precision=None):
+    """``prep_data_for_PR`` on the GPU for unsigned 16-bit stacks; returns a CUDA tensor (nz, xysize, xysize).
+
+    ``data`` is a uint16 numpy array or CUDA tensor (nz, ny, nx).  Histogram mode, arg-max, roll / pad / crop and the
+    clip run on the device (``pyotf_b200_prep_data_u16``); values are bit-identical to the host function in fp64.
+    The result can be handed to ``retrieve_phase`` directly, so a measured stack never visits the host as floats.
+    """
+    import ctypes as C
+
+    from . import _engine, _lib
+
+    torch = _engine._torch()
+    prec = precision or _engine.get_precision()
+    if isinstance(data, np.ndarray):
+        if data.dtype != np.uint16:
+            raise ValueError("prep_data_for_PR_dev handles uint16 stacks; use prep_data_for_PR for other dtypes")
+        dev = torch.as_tensor(np.ascontiguousarray(data).view(np.int16), device="cuda")
+    else:
+        dev = data.contiguous()
+        if dev.dtype not in (torch.uint16, torch.int16):
+            raise ValueError("prep_data_for_PR_dev handles uint16 stacks")
+    nz, ny, nx = (int(v) for v in dev.shape)
+    size = max(ny, nx) if xysize is None else int(xysize)
+    out = torch.empty((nz, size, size), dtype=torch.float32 if prec == "fp32" else torch.float64, device="cuda")
+    mode = C.c_int(0)
+    _lib.check(_lib.load().pyotf_b200_prep_data_u16(_engine.ptr(dev), nz, ny, nx, size, float(multiplier),
+                                                    _engine.dtype_code(prec), _engine.ptr(out), C.byref(mode),
+                                                    _engine.stream_ptr()))
+    return out
+
+
 def prep_data_for_PR(data, xysize=None, multiplier=1.05):
     """Background-subtract, pad/crop to ``xysize`` and clip at zero (pyotf/utils.py:161-201)."""
     nz, ny, nx = data.shape
