@@ -139,3 +139,29 @@ def test_streaming_mode_is_bit_identical():
     for k in range(6):
         assert torch.equal(outs[k], ref[k]), k
     assert torch.equal(same, ref[-1])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_wide_support_high_na(precision):
+    """High-NA optics at coarse sampling: the pupil box (K = 149 at 256^2) is too large for the staged defocus
+    table, so K1 / K2 evaluate the defocus on the fly and pick 32 rows per CTA; same parity bar."""
+    from oracle import pyotf_oracle as orc
+    from pyotf_b200 import _engine as eng
+    from pyotf_b200.phaseretrieval import retrieve_phase
+
+    wl, na, ni, res, size = 488, 1.4, 1.518, 100, 256
+    z = np.array([-800.0, -150.0, 90.0, 610.0])
+    h = eng.hanser_handle(wl, na, ni, res, size, "none", "sine", precision, -1)
+    assert h.K >= 147
+    for vc, cond in (("none", "sine"), ("total", "herschel")):
+        psfa, psfi = _run(precision, wl, na, ni, res, size, z, vc, cond)
+        ref = orc.hanser_psfa(wl, na, ni, res, size, z, vc, cond)
+        assert rel_l2(psfa, ref) <= TOL[precision]
+        assert rel_l2(psfi, orc.psfi(ref)) <= TOL[precision]
+    rng = np.random.default_rng(1)
+    pupil = orc.aberrated_pupil(wl, na, ni, res, size, rng.random(12) * 0.1, rng.random(12))
+    data = orc.psfi(orc.hanser_psfa(wl, na, ni, res, size, z + 33.0, "none", "none", pupil)) * 1e4
+    o = orc.retrieve_phase_loop(data, wl, na, ni, res, zrange=z + 33.0, max_iters=6, pupil_tol=0, mse_tol=0)
+    r = retrieve_phase(data, dict(wl=wl, na=na, ni=ni, res=res, zrange=z + 33.0), 6, 0, 0, precision=precision)
+    assert rel_l2(r.mse, o["mse"]) <= TOL[precision]
+    assert rel_l2(r.pupil, o["pupil"]) <= (1e-11 if precision == "fp64" else 2e-5)
