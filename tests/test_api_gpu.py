@@ -276,3 +276,28 @@ def test_utils():
         assert rel_l2(easy_fft(a.real, axes), fftshift(fftn(ifftshift(a.real, axes=axes), axes=axes), axes=axes)) <= 1e-12
         a32 = a.astype(np.complex64)
         assert rel_l2(easy_fft(a32, axes), fftshift(fftn(ifftshift(a, axes=axes), axes=axes), axes=axes)) <= 2e-6
+
+
+def test_library_and_stack_edge_cases():
+    """Single-entry and several-hundred-entry libraries, one-plane and 1000-plane stacks, scalar zrange."""
+    from oracle import pyotf_oracle as orc
+    from pyotf_b200.otf import HanserPSF, psf_library
+
+    kw = dict(wl=520, na=0.85, ni=1.0, res=130)
+    base = HanserPSF(size=64, zres=300, zsize=3, precision="fp64", **kw)
+    coefs = np.random.default_rng(5).standard_normal((300, 21)) * 0.2
+    lib = psf_library(base, coefs).cpu().numpy()
+    assert lib.shape == (300, 3, 64, 64)
+    for b in (0, 137, 299):
+        pupil = orc.aberrated_pupil(kw["wl"], kw["na"], kw["ni"], kw["res"], 64, None, coefs[b])
+        ref = orc.psfi(orc.hanser_psfa(kw["wl"], kw["na"], kw["ni"], kw["res"], 64, base.zrange, pupil_base=pupil))
+        assert rel_l2(lib[b], ref) <= 1e-11
+    one = psf_library(base, coefs[7]).cpu().numpy()
+    assert one.shape == (1, 3, 64, 64) and rel_l2(one[0], lib[7]) == 0.0
+    with pytest.raises(ValueError):
+        psf_library(base, None)
+    long_stack = HanserPSF(size=32, zres=50, zsize=1000, precision="fp32", **kw)
+    ref = orc.psfi(orc.hanser_psfa(kw["wl"], kw["na"], kw["ni"], kw["res"], 32, long_stack.zrange))
+    assert long_stack.PSFi.shape == (1000, 32, 32) and rel_l2(long_stack.PSFi, ref) <= 1e-5
+    single = HanserPSF(size=128, zrange=250.0, precision="fp64", **kw)
+    assert rel_l2(single.PSFi, orc.psfi(orc.hanser_psfa(kw["wl"], kw["na"], kw["ni"], kw["res"], 128, [250.0]))) <= 1e-11

@@ -270,3 +270,22 @@ def test_fit_to_zernikes_device_normal_equations_vs_host_lstsq():
     assert rel_l2(zd.phase(slice(4, None)), _recon_from_zerns(ref_p[4:], zerns[4:])) <= 1e-9
     assert zd.complex_pupil().shape == (256, 256) and np.isfinite(zd.rms_error)
     assert r.generate_zd_psf().shape == (25, 256, 256)
+
+
+@pytest.mark.parametrize("size,nz", [(64, 1), (64, 300), (256, 70), (32, 2)])
+def test_stack_length_edge_cases(size, nz):
+    """One plane, and stacks long enough for several waves of plane kernels / the narrow-CTA variant."""
+    from oracle import pyotf_oracle as orc
+    from pyotf_b200.phaseretrieval import retrieve_phase
+
+    rng = np.random.default_rng(nz)
+    z = (np.arange(nz) - nz // 2) * 110.0 + 17.0
+    pupil = orc.aberrated_pupil(OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], size, rng.random(8) * 0.1, rng.random(8))
+    data = orc.psfi(orc.hanser_psfa(OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], size, z, "none", "none", pupil)) * 1e4
+    params = dict(wl=OPT["wl"], na=OPT["na"], ni=OPT["ni"], res=OPT["res"], zrange=z)
+    o = orc.retrieve_phase_loop(data, OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], zrange=z, max_iters=5, pupil_tol=0,
+                                mse_tol=0)
+    for precision, tol in (("fp64", 1e-11), ("fp32", 1e-5)):
+        r = retrieve_phase(data, dict(params), 5, 0, 0, precision=precision)
+        assert rel_l2(r.mse, o["mse"]) <= tol
+        assert rel_l2(r.pupil, o["pupil"]) <= 2 * tol
