@@ -384,7 +384,10 @@ template <typename T, int N, int M, int TABM, bool SYM>
 __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
     constexpr bool TAB = TABM != 0;
     static_assert(!SYM || TAB, "the symmetric path needs the (symmetric-box) table");
-    pdl_launch_dependents();          // a following K1 launch may start filling the SMs this grid leaves idle
+    pdl_launch_dependents();          // a following K1 launch may be scheduled while this grid drains
+    // default: wait for the preceding kernel before reading anything (only the launch latency overlaps);
+    // streaming mode: wait only before the first global store (the whole compute phase overlaps)
+    if (!a.overlap) pdl_wait();
     using RP = FftPlan<N>;
     using CP = FftPlan<M>;
     using SM = HanserSmem<N, M, T>;
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
         // ---------------- rows: FFT_N over kx + epilogue ----------------
         // everything so far read per-handle constants and wrote shared memory only; the stores below must
         // not overtake those of an earlier launch into the same buffers (no-op for ordinary launches)
-        if (v == 0) pdl_wait();
+        if (v == 0 && a.overlap) pdl_wait();
         {
             constexpr int R1 = RP::R1, L1 = RP::R2, G = RP::G, NG = SM::NG, PITCH = SM::PITCH;
             constexpr int CL1 = CP::R2, CQ1 = CP::R1;

@@ -88,11 +88,12 @@ int hanser_launch_nmt(const HanserArgs<T>& a, int batch, size_t smem, cudaStream
         attr[0].val.clusterDim.x = N / M; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         PYOTF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
-    } else if (TABM == 3 && a.pupilc == nullptr && a.overlap) {
-        // streaming mode (pyotf_b200_hanser_set_overlap): the caller promises that nothing this launch reads
-        // (z_dev; the handle's tables are immutable) is written by the kernel that precedes it in the stream, so
-        // back-to-back launches overlap (programmatic dependent launch; the kernel still waits for its
-        // predecessor right before its first global store, so output order is preserved)
+    } else if (TABM == 3 && a.pupilc == nullptr) {
+        // programmatic dependent launch: back-to-back stacks overlap.  Default: the kernel waits for its
+        // predecessor before it reads anything, so only the launch latency is hidden and no assumption is made.
+        // Streaming mode (pyotf_b200_hanser_set_overlap): the caller promises that nothing this launch reads
+        // (z_dev; the handle's tables are immutable) is written by the kernel that precedes it in the stream; the
+        // kernel then waits only right before its first global store, so the whole compute phase overlaps too.
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid; cfg.blockDim = dim3(SM::NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
         cudaLaunchAttribute attr[1];
