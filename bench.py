@@ -227,6 +227,16 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100):
            "rows_per_cta": st.rows_per_cta, "ctas_per_iteration": st.nparts,
            "kernels_per_iteration": 2 if world == 1 else 4, "final_mse": float(mse[-1]),
            "parallelism": f"z-shard x{world}" + ("" if world == 1 else " + 1 NCCL all-reduce / iteration")}
+    # roofline of one iteration: nz*N^2*s_r of measured data + 2 compact... full-grid pupils (in/out)
+    es = 4 if precision == "fp32" else 8
+    alg = nz_total * 256 * 256 * es + 2 * 256 * 256 * 2 * es
+    peak, peak_src = measured_peaks()
+    out["roofline"] = {"bound": "hbm", "achieved": alg / (best * 1e-3 / iters) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": alg / (best * 1e-3 / iters) / 1e9 / peak, "algorithmic_bytes_per_iteration": alg,
+                       "kernel": "pr_plane_kernel + pr_finalize_kernel", "peak_source": peak_src,
+                       "note": "the 7.6 MB working set of an iteration is L2-resident (ncu: 7.4 MB of DRAM reads per "
+                               "plane-kernel launch only because ncu flushes caches), so HBM is not the binding limit: "
+                               "the plane kernel is instruction-issue / latency bound on the 100 SMs its 100 CTAs occupy"}
     if world == 1:
         # end to end through the public API: host stack in, PhaseRetrievalResult (host arrays) out
         params = dict(PR_PARAMS)
