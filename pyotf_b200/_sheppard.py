@@ -29,19 +29,15 @@ def otfa(model):
 
 
 def _fused(model, want_psfa, want_psfi):
-    """One pyotf_b200_sheppard_psf call; fills the model's device cache with everything it produced."""
+    """One pyotf_b200_sheppard_psf call without OTFa: the shell is generated inside the first FFT pass."""
     torch = _engine._torch()
     rt, ct = _engine.torch_dtypes(model.precision)
     shape = (_nvec(model), model.zsize, model.size, model.size)
-    dev = model.__dict__.setdefault("_device", {})
-    otf = torch.empty(shape, dtype=ct, device="cuda")
     psfa_t = torch.empty(shape, dtype=ct, device="cuda") if want_psfa else None
     psfi_t = torch.empty(shape[1:], dtype=rt, device="cuda") if want_psfi else None
     p = _params(model)
-    _lib.check(_lib.load().pyotf_b200_sheppard_psf(C.byref(p), _engine.ptr(otf), _engine.ptr(psfa_t), _engine.ptr(psfi_t),
+    _lib.check(_lib.load().pyotf_b200_sheppard_psf(C.byref(p), C.c_void_p(0), _engine.ptr(psfa_t), _engine.ptr(psfi_t),
                                                    _engine.stream_ptr()))
-    if not model._has_result("OTFa"):
-        dev["OTFa"] = otf
     return psfa_t, psfi_t
 
 

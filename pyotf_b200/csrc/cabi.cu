@@ -307,6 +307,9 @@ int pyotf_b200_sheppard_psf(const pyotf_sheppard_params* q, void* otfa_out, void
     unsigned char* flags = nullptr;         // rowflag [NZ*N] | planeflag [NZ] | f_x [nlines] | f_y [nlines]
     const bool want_fft = psfa_out || psfi_out;
     keep_scratch_pool();
+    if (!otfa_out)       // OTFa not wanted: generate the shell inside the first FFT pass, fuse |.|^2 into the last
+        return q->dtype == PYOTF_F32 ? sheppard_fused<float>(p, psfa_out, psfi_out, s)
+                                     : sheppard_fused<double>(p, psfa_out, psfi_out, s);
     if (!otfa) PYOTF_CUDA_OK(cudaMallocAsync(&otfa, nvox * p.nvec * 2 * es, s));
     if (want_fft) {
         PYOTF_CUDA_OK(cudaMallocAsync(&flags, (size_t)p.NZ * p.N + p.NZ + 2 * nlines, s));

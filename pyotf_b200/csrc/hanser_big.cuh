@@ -49,6 +49,17 @@ __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nline
     if (threadIdx.x < nlines) sline[threadIdx.x] = f.info(line0 + threadIdx.x);
     for (int k = threadIdx.x; k < Lr; k += blockDim.x) tw[k] = f.twiddle(k);   // e^{+2 pi i k / L}, precomputed
     __syncthreads();
+    if constexpr (F::HAS_EMPTY) {                      // all lines of the tile known to be zero: no transform
+        bool any = false;
+        for (int t = 0; t < nlines; ++t) any |= !f.empty(sline[t]);     // CTA-uniform
+        if (!any) {
+            for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
+                const int t = LINE_MAJOR ? w / Lr : w % nlines, o = LINE_MAJOR ? w % Lr : w / nlines;
+                f.zero_fill(sline[t], o);
+            }
+            return;
+        }
+    }
     if (LINE_MAJOR) {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int t = w / Lr, l = w - t * Lr;
@@ -115,6 +126,7 @@ __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nline
 
 // functors without a reduction / early exit
 struct NoAcc {
+    static constexpr bool HAS_EMPTY = false;          // functors that can prove a line is all-zero override this
     using Acc = int;
     __device__ __forceinline__ static Acc acc_init() { return 0; }
     __device__ __forceinline__ void finish(Acc) const {}

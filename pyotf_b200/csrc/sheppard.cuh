@@ -19,6 +19,9 @@ struct SheppardParams {
     double r2_lo, r2_hi;      // conservative bounds on kr^2 for a voxel to be on the shell (prefilter)
 };
 
+// fused PSFa / PSFi path (sheppard_impl.cuh, instantiated in sheppard_f32.cu / sheppard_f64.cu)
+template <typename T> int sheppard_fused(const SheppardParams& p, void* psfa_out, void* psfi_out, cudaStream_t s);
+
 __device__ __forceinline__ double fftfreq_at(int i, int n, double step) {
     // numpy.fft.fftfreq: integers [0, ..., (n-1)//2, -(n//2), ..., -1] * (1 / (n d))
     int f = i < (n + 1) / 2 ? i : i - n;

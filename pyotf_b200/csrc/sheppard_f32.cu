@@ -1,0 +1,4 @@
+#include "sheppard_impl.cuh"
+namespace pyotf {
+template int sheppard_fused<float>(const SheppardParams&, void*, void*, cudaStream_t);
+}  // namespace pyotf

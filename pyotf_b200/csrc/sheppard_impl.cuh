@@ -1,0 +1,201 @@
+// K3 fused path: SheppardPSF.PSFa / .PSFi without materialising the amplitude OTF (pyotf/otf.py:535-592,
+// :204-207).  easy_ifft(OTFa, axes=(1,2,3)) is evaluated as three line passes:
+//   pass 1 (x, contiguous): the shell values of a (kz, ky) row are generated on the fly inside the load
+//           (same fp64 predicates as sheppard_otf_kernel); rows that cannot touch the shell are zero-filled
+//           without any transform (the shell occupies 17 % of the rows of 34 % of the planes at config 3)
+//   pass 2 (y): the generic axis pass, skipping planes that cannot hold shell voxels
+//   pass 3 (z): transform + 1/n scaling + |.|^2 accumulated over the polarisation components into PSFi
+//           (and / or the PSFa store), so neither OTFa nor a separate |.|^2 pass touches HBM.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "hanser_impl.cuh"
+#include "sheppard.cuh"
+
+namespace pyotf {
+
+template <typename T> struct ShepArgs {
+    SheppardParams p;
+    int v;                      // polarisation component handled by this launch
+    int in_x, out_x;            // shifts of pass 1 (see AxisPass)
+    int in_z, out_z;            // shifts of pass 3
+    cplx<T>* tmp;               // [NZ][N][N] of component v
+    cplx<T>* psfa;              // [NZ][N][N] of component v or nullptr
+    T* psfi;                    // [NZ][N][N] or nullptr
+    const cplx<T>* tw_x;        // [N]
+    const cplx<T>* tw_z;        // [NZ]
+    const unsigned char* planeflag;   // [NZ][N]: 1 where the (memory-layout) plane zm can hold shell voxels
+    int accumulate;
+    double scale;
+};
+
+// value of polarisation component v on a shell voxel (otf.py:542-575); scalar model: 1
+template <typename T>
+__device__ __forceinline__ T sheppard_value(const SheppardParams& p, int v, double kz, double ky, double kx) {
+    if (p.vec_mode == 0) return (T)1;
+    const double kn = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(kx, kx), __dmul_rn(ky, ky)), __dmul_rn(kz, kz)));
+    const double m = kx / kn, n = ky / kn, s = kz / kn;
+    double a = 1.0;
+    if (p.condition == 1) a = 1.0 / sqrt(s);
+    else if (p.condition == 2) a = 1.0 / s;
+    // component order: z -> (Pzx, Pzy), y -> (Pyx, Pyy), x -> (Pxx, Pxy); "total" = all six in that order
+    int c = v;
+    if (p.vec_mode == 2) c = v + 2;
+    else if (p.vec_mode == 1) c = v + 4;
+    double val;
+    switch (c) {
+        case 0: val = -m; break;
+        case 1: val = -n; break;
+        case 2: val = -n * m / (1 + s); break;
+        case 3: val = 1 - n * n / (1 + s); break;
+        case 4: val = 1 - m * m / (1 + s); break;
+        default: val = -m * n / (1 + s); break;
+    }
+    return (T)(val * a);
+}
+
+// planeflag[zm][x] = 1 iff the plane with memory index zm (fftshift-ed layout) can hold shell voxels:
+// kzz > kz_min (valid needs kzz > kz_min + dkr, dkr >= 0) and |kz| <= kmag + max(dk, dkz) (since |kz| <= kr)
+static __global__ void sheppard_planeflag_kernel(SheppardParams p, unsigned char* __restrict__ flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)p.NZ * p.N) return;
+    const int zm = (int)(i / p.N);
+    int zu = zm - p.NZ / 2; if (zu < 0) zu += p.NZ;
+    const double kz = fftfreq_at(zu, p.NZ, p.kzstep);
+    const double kzz = p.dual ? fabs(kz) : kz;
+    const double dmax = fmax(fabs(p.dk), fabs(p.dkz));
+    flag[i] = (kzz > p.kz_min && fabs(kz) <= (p.kmag + dmax) * (1.0 + 1e-9)) ? 1 : 0;
+}
+
+// ---- pass 1: line = (zm, ym) in the fftshift-ed memory layout, axis = x ---------------------------------
+template <typename T> struct ShepRow : NoAcc {
+    static constexpr bool HAS_EMPTY = true;
+    struct Line { double kz, ky, r2zy; cplx<T>* out; int maybe, plane_maybe; };
+    ShepArgs<T> a;
+    __device__ __forceinline__ cplx<T> twiddle(int k) const { return a.tw_x[k]; }
+    __device__ __forceinline__ Line info(long long line) const {
+        const SheppardParams& p = a.p;
+        const int ym = (int)(line % p.N), zm = (int)(line / p.N);
+        int yu = ym - p.N / 2; if (yu < 0) yu += p.N;               // OTFa[j] = otf[(j - n//2) mod n]
+        int zu = zm - p.NZ / 2; if (zu < 0) zu += p.NZ;
+        Line d;
+        d.kz = fftfreq_at(zu, p.NZ, p.kzstep);
+        d.ky = fftfreq_at(yu, p.N, p.kstep);
+        d.r2zy = __dadd_rn(__dmul_rn(d.kz, d.kz), __dmul_rn(d.ky, d.ky));
+        d.out = a.tmp + (size_t)line * p.N;
+        // can any voxel of this row lie on the shell?  (conservative: the exact predicate runs per voxel)
+        const double kxmax = p.kstep * (double)(p.N / 2);
+        const double kzz = p.dual ? fabs(d.kz) : d.kz;
+        d.plane_maybe = a.planeflag[(size_t)zm * p.N];
+        d.maybe = d.plane_maybe && d.r2zy <= p.r2_hi && d.r2zy + kxmax * kxmax >= p.r2_lo && kzz > p.kz_min;
+        return d;
+    }
+    __device__ __forceinline__ bool empty(const Line& d) const { return !d.maybe; }
+    // rows of planes that cannot hold the shell are neither transformed nor zero-filled: passes 2 and 3 skip them
+    __device__ __forceinline__ void zero_fill(const Line& d, int o) const { if (d.plane_maybe) d.out[o] = mk<T>(0, 0); }
+    __device__ __forceinline__ cplx<T> load(const Line& d, int l) const {
+        const SheppardParams& p = a.p;
+        int xm = l + a.in_x; if (xm >= p.N) xm -= p.N;             // x_in[l] = OTFa[(l + in_shift) mod n]
+        int xu = xm - p.N / 2; if (xu < 0) xu += p.N;
+        const double kx = fftfreq_at(xu, p.N, p.kstep);
+        const double kr2 = __dadd_rn(d.r2zy, __dmul_rn(kx, kx));   // ((kz^2 + ky^2) + kx^2): numpy's order
+        if (kr2 < p.r2_lo || kr2 > p.r2_hi) return mk<T>(0, 0);
+        const double kr = sqrt(kr2);
+        double dkr;
+        if (p.same_dk) dkr = p.dk;
+        else if (kr2 == 0.0) dkr = 0.0;
+        else {
+            const double aa = __dmul_rn(d.kz, p.dkz), bb = __dmul_rn(d.ky, p.dk), cc = __dmul_rn(kx, p.dk);
+            dkr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(aa, aa), __dmul_rn(bb, bb)), __dmul_rn(cc, cc))) / kr;
+        }
+        const double kzz = p.dual ? fabs(d.kz) : d.kz;
+        const bool valid = (fabs(__dsub_rn(kr, p.kmag)) < dkr) && (kzz > __dadd_rn(p.kz_min, dkr));
+        if (!valid) return mk<T>(0, 0);
+        return mk<T>(sheppard_value<T>(p, a.v, d.kz, d.ky, kx), 0);
+    }
+    __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v, int&) const {
+        int xm = o + a.out_x; if (xm >= a.p.N) xm -= a.p.N;
+        d.out[xm] = cscale(v, (T)a.scale);
+    }
+};
+
+// ---- pass 3: line = (ym, xm), axis = z --------------------------------------------------------------------
+template <typename T> struct ShepCol : NoAcc {
+    struct Line { const cplx<T>* in; cplx<T>* psfa; T* psfi; };
+    ShepArgs<T> a;
+    __device__ __forceinline__ cplx<T> twiddle(int k) const { return a.tw_z[k]; }
+    __device__ __forceinline__ Line info(long long line) const {
+        Line d;
+        d.in = a.tmp + line;
+        d.psfa = a.psfa ? a.psfa + line : nullptr;
+        d.psfi = a.psfi ? a.psfi + line : nullptr;
+        return d;
+    }
+    __device__ __forceinline__ cplx<T> load(const Line& d, int l) const {
+        int zm = l + a.in_z; if (zm >= a.p.NZ) zm -= a.p.NZ;
+        if (!a.planeflag[(size_t)zm * a.p.N]) return mk<T>(0, 0);     // never written: the plane holds no shell voxel
+        return d.in[(size_t)zm * a.p.N * a.p.N];
+    }
+    __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v, int&) const {
+        int zm = o + a.out_z; if (zm >= a.p.NZ) zm -= a.p.NZ;
+        const size_t off = (size_t)zm * a.p.N * a.p.N;
+        v = cscale(v, (T)a.scale);
+        if (d.psfa) d.psfa[off] = v;
+        if (d.psfi) {
+            const T I = v.x * v.x + v.y * v.y;
+            if (a.accumulate) d.psfi[off] += I; else d.psfi[off] = I;       // otf.py:204-207
+        }
+    }
+};
+
+int fft_twiddles_f32(int L, const void** out, cudaStream_t s);   // fftnd_f32.cu / fftnd_f64.cu
+int fft_twiddles_f64(int L, const void** out, cudaStream_t s);
+
+template <typename T>
+int sheppard_fused(const SheppardParams& p, void* psfa_out, void* psfi_out, cudaStream_t s) {
+    int dev = 0, smem_limit = 0;
+    PYOTF_CUDA_OK(cudaGetDevice(&dev));
+    PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    keep_scratch_pool();
+    const size_t nvox = (size_t)p.NZ * p.N * p.N;
+    cplx<T>* tmp = nullptr;
+    unsigned char* planeflag = nullptr;
+    PYOTF_CUDA_OK(cudaMallocAsync(&tmp, nvox * sizeof(cplx<T>), s));
+    PYOTF_CUDA_OK(cudaMallocAsync(&planeflag, (size_t)p.NZ * p.N, s));
+    // line flags of passes 2 / 3: line (zm, xm) may hold data iff plane zm may hold shell voxels
+    sheppard_planeflag_kernel<<<(unsigned)(((size_t)p.NZ * p.N + 255) / 256), 256, 0, s>>>(p, planeflag);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    ShepArgs<T> a;
+    a.p = p; a.tmp = tmp; a.planeflag = planeflag;
+    const void *twx = nullptr, *twz = nullptr;
+    int rc = sizeof(T) == 4 ? fft_twiddles_f32(p.N, &twx, s) : fft_twiddles_f64(p.N, &twx, s);
+    if (!rc) rc = sizeof(T) == 4 ? fft_twiddles_f32(p.NZ, &twz, s) : fft_twiddles_f64(p.NZ, &twz, s);
+    a.tw_x = (const cplx<T>*)twx; a.tw_z = (const cplx<T>*)twz;
+    // easy_ifft = ifftshift(ifftn(fftshift(.))): per axis in_shift = n - n//2 ... see fftn_run (inverse, both shifts)
+    auto shifts = [](int L, int& in, int& out) { const int half = L / 2, rest = (L - half) % L; in = rest; out = rest; };
+    shifts(p.N, a.in_x, a.out_x);
+    shifts(p.NZ, a.in_z, a.out_z);
+    for (int v = 0; v < p.nvec && !rc; ++v) {
+        a.v = v; a.accumulate = v > 0;
+        a.psfa = psfa_out ? (cplx<T>*)psfa_out + (size_t)v * nvox : nullptr;
+        a.psfi = (T*)psfi_out;
+        a.scale = 1.0 / (double)p.N;
+        ShepRow<T> f1; f1.a = a;
+        rc = fft_lines_launch<1, T, true>(p.N, (long long)p.NZ * p.N, f1, smem_limit, s);
+        if (rc) break;
+        const long long shape[3] = {p.NZ, p.N, p.N};
+        const int axes[1] = {1};
+        const unsigned char* pf[1] = {planeflag};
+        rc = fftn_run<T>(tmp, tmp, 3, shape, axes, 1, 1, 0, 1, 1, s, pf);
+        if (rc) break;
+        a.scale = 1.0 / (double)p.NZ;
+        ShepCol<T> f3; f3.a = a;
+        rc = fft_lines_launch<1, T, false>(p.NZ, (long long)p.N * p.N, f3, smem_limit, s);
+    }
+    cudaFreeAsync(planeflag, s);
+    cudaFreeAsync(tmp, s);
+    return rc;
+}
+
+}  // namespace pyotf

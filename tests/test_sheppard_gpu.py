@@ -31,6 +31,10 @@ def test_small_golden_and_oracle(precision, vc, cond, dual):
     assert np.array_equal(s.OTFa != 0, o != 0)                      # the shell predicate is exact
     assert rel_l2(s.PSFa, orc.sheppard_psfa(o)) <= tol
     assert rel_l2(s.OTFi, orc.otfi(orc.psfi(orc.sheppard_psfa(o)))) <= tol
+    # a fresh model asked for PSFa first takes the fused path (shell generated inside the first FFT pass)
+    s2 = SheppardPSF(vec_corr=vc, condition=cond, dual=dual, precision=precision, **SK)
+    assert rel_l2(s2.PSFa, orc.sheppard_psfa(o)) <= tol
+    assert rel_l2(s2.PSFi, s.PSFi) <= tol
     s._gen_kr()
     assert int(s.valid_points.sum()) == int(g[f"nshell_{tag}"])
     valid, kzz, kyy, kxx, dk, dkz = orc.sheppard_shell(SK["wl"], SK["na"], SK["ni"], SK["res"], SK["size"], SK["zres"],
@@ -53,8 +57,11 @@ def test_same_dk_branch_and_odd_sizes():
                dict(wl=520, na=1.1, ni=1.33, res=90, size=27, zres=150, zsize=15)):
         s = SheppardPSF(precision="fp64", **kw)
         o = orc.sheppard_otfa(kw["wl"], kw["na"], kw["ni"], kw["res"], kw["size"], kw["zres"], kw["zsize"])
+        fused = SheppardPSF(precision="fp64", **kw)
+        assert rel_l2(fused.PSFi, orc.psfi(orc.sheppard_psfa(o))) <= 1e-11      # fused path (no OTFa yet)
+        assert rel_l2(fused.PSFa, orc.sheppard_psfa(o)) <= 1e-11
         assert np.array_equal(s.OTFa, o)
-        assert rel_l2(s.PSFi, orc.psfi(orc.sheppard_psfa(o))) <= 1e-11
+        assert rel_l2(s.PSFi, orc.psfi(orc.sheppard_psfa(o))) <= 1e-11          # generator + 3-pass path
 
 
 def test_api_semantics():
