@@ -9,6 +9,9 @@
 #include <cstdint>
 #include <numeric>
 #include <vector>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -20,21 +23,12 @@ inline int jump(double a, double b) { double d = a - b; return d > PI ? 1 : (d <
 struct UnionFind {
     std::vector<int> parent, size, pot;   // pot[p] = n[p] - n[parent[p]] in units of 2 pi
     explicit UnionFind(int n) : parent(n), size(n, 1), pot(n, 0) { std::iota(parent.begin(), parent.end(), 0); }
-    std::vector<int> path;
-    int find(int p, int& acc) {           // returns root, acc = n[p] - n[root]; compresses the path
-        path.clear();
-        int cur = p;
-        while (parent[cur] != cur) { path.push_back(cur); cur = parent[cur]; }
-        const int root = cur;
+    // union by size keeps every tree O(log n) deep, so a plain walk (no path compression, no writes) is fastest
+    int find(int p, int& acc) const {     // returns root, acc = n[p] - n[root]
         int total = 0;
-        for (int i = (int)path.size() - 1; i >= 0; --i) {   // from the node next to the root outwards
-            const int node = path[i];
-            total += pot[node];
-            pot[node] = total;
-            parent[node] = root;
-        }
+        while (parent[p] != p) { total += pot[p]; p = parent[p]; }
         acc = total;
-        return root;
+        return p;
     }
 };
 }  // namespace
@@ -42,6 +36,9 @@ struct UnionFind {
 extern "C" int pyotf_b200_unwrap_phase_2d(const double* in, double* out, int ny, int nx) {
     PYOTF_REQUIRE(in && out && ny > 0 && nx > 0, "unwrap_phase_2d: bad argument");
     const int n = ny * nx;
+    const bool prof = getenv("PYOTF_UNWRAP_PROFILE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (prof) { auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "unwrap %s: %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count()); t0 = t1; } };
     std::vector<double> v(n), rel(n);
     for (int i = 0; i < n; ++i) v[i] = wrap(in[i]);   // already in [-pi, pi] for np.angle output
     for (int y = 0; y < ny; ++y)
@@ -58,6 +55,7 @@ extern "C" int pyotf_b200_unwrap_phase_2d(const double* in, double* out, int ny,
             const double D2 = wrap(v[i - nx + 1] - c) - wrap(c - v[i + nx - 1]);
             rel[i] = H * H + V * V + D1 * D1 + D2 * D2;
         }
+    lap("reliability");
     struct Edge { double r; int a, b; };
     std::vector<Edge> edges;
     edges.reserve((size_t)2 * n);
@@ -67,11 +65,13 @@ extern "C" int pyotf_b200_unwrap_phase_2d(const double* in, double* out, int ny,
             if (x + 1 < nx) edges.push_back({rel[i] + rel[i + 1], i, i + 1});
             if (y + 1 < ny) edges.push_back({rel[i] + rel[i + nx], i, i + nx});
         }
+    lap("edges");
     // ascending reliability, ties in generation order.  Most edges of a retrieved pupil lie in the zero
     // region outside the aperture (reliability exactly 0): they are moved to the front unsorted and only the
     // rest is sorted -- the same order a stable sort of everything would give.
     auto mid = std::stable_partition(edges.begin(), edges.end(), [](const Edge& e) { return e.r == 0.0; });
     std::stable_sort(mid, edges.end(), [](const Edge& p, const Edge& q) { return p.r < q.r; });
+    lap("sort");
     UnionFind uf(n);
     for (const Edge& e : edges) {
         int pa, pb;
@@ -82,6 +82,7 @@ extern "C" int pyotf_b200_unwrap_phase_2d(const double* in, double* out, int ny,
         if (uf.size[ra] > uf.size[rb]) { uf.parent[rb] = ra; uf.pot[rb] = nrb_minus_nra; uf.size[ra] += uf.size[rb]; }
         else { uf.parent[ra] = rb; uf.pot[ra] = -nrb_minus_nra; uf.size[rb] += uf.size[ra]; }
     }
+    lap("union");
     for (int i = 0; i < n; ++i) {
         int acc;
         uf.find(i, acc);
