@@ -381,7 +381,7 @@ __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const 
 // only the rows y <= N/2 are transformed, each stored to y and to N - y.  Halves both halves of the work
 // for the reference's default model (HanserPSF with no aberration), bit-identical otherwise.
 template <typename T, int N, int M, int TABM, bool SYM>
-__global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
+__global__ void __launch_bounds__(256, (M == 128 ? 2 : 0)) hanser_psf_kernel(HanserArgs<T> a) {
     constexpr bool TAB = TABM != 0;
     static_assert(!SYM || TAB, "the symmetric path needs the (symmetric-box) table");
     pdl_launch_dependents();          // a following K1 launch may be scheduled while this grid drains
@@ -397,6 +397,10 @@ __global__ void __launch_bounds__(256) hanser_psf_kernel(HanserArgs<T> a) {
     cplx<T>* tws = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* U = tws + N;
     cplx<T>* EX = U + (size_t)M * a.KP;
+    // SYM: only the columns fx >= 0 (kx >= -f0) exist; the host passes the compact pitch in a.KP and every
+    // access below keeps its absolute column index kx through this bias (half the work area: 128 rows per CTA
+    // fit two CTAs per SM at 256^2)
+    if constexpr (SYM) U += a.f0;
 
     const int tid = threadIdx.x;
     const int r = blockIdx.x % R;

@@ -108,6 +108,25 @@ int hanser_launch_nmt(const HanserArgs<T>& a, int batch, size_t smem, cudaStream
     return 0;
 }
 
+// pitch of the compact work area of the even-symmetric variant (columns fx = 0 .. -f0 only), same residue
+// rule as the full pitch (cabi.cu)
+inline int hanser_sym_pitch(int f0) { const int nc = 1 - f0; return nc + ((8 - nc % 16) + 16) % 16; }
+
+template <typename T> bool hanser_use_sym(const HanserArgs<T>& a) {
+    // ideal pupil of the scalar model: the even-symmetric variant (half the columns, half the rows)
+    static const bool no_sym = getenv("PYOTF_B200_K1_NOSYM") != nullptr;
+    return a.amp_in_tab && !no_sym;
+}
+
+// 128 rows per CTA (256^2 only, even-symmetric variant only: its compact work area lets two CTAs share an SM):
+// the fold and the per-CTA defocus table are paid twice per plane instead of four times
+template <typename T, int N>
+int hanser_launch_sym128(const HanserArgs<T>& a, int tabm, int batch, cudaStream_t s) {
+    const size_t smem = HanserSmem<N, 128, T>::bytes(a.KP);
+    if (tabm == 3) return hanser_launch_nmt<T, N, 128, 3, true>(a, batch, smem, s);
+    return hanser_launch_nmt<T, N, 128, 1, true>(a, batch, smem, s);
+}
+
 template <typename T, int N, int M>
 int hanser_launch_nm(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int batch, cudaStream_t s) {
     size_t smem = HanserSmem<N, M, T>::bytes(a.KP);
@@ -116,9 +135,7 @@ int hanser_launch_nm(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, in
         if constexpr (N / M <= 8) return hanser_launch_nmt<T, N, M, 2>(a, batch, smem, s);
     }
 #endif
-    // ideal pupil of the scalar model: the even-symmetric variant (half the columns, half the rows)
-    static const bool no_sym = getenv("PYOTF_B200_K1_NOSYM") != nullptr;
-    const bool sym = a.amp_in_tab && !no_sym;
+    const bool sym = hanser_use_sym(a);
     if (tabm == 3) return sym ? hanser_launch_nmt<T, N, M, 3, true>(a, batch, smem, s) : hanser_launch_nmt<T, N, M, 3>(a, batch, smem, s);
     if (tabm == 1) return sym ? hanser_launch_nmt<T, N, M, 1, true>(a, batch, smem, s) : hanser_launch_nmt<T, N, M, 1>(a, batch, smem, s);
     return hanser_launch_nmt<T, N, M, 0>(a, batch, smem, s);
@@ -132,13 +149,14 @@ template <typename T, int N> size_t hanser_smem_for(int M, int KP) {
 
 // picks rows-per-CTA M; *m_out receives it when only the choice is wanted (launch = false)
 template <typename T, int N>
-int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int batch, int smem_limit, cudaStream_t s,
+int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a_in, int tabm, int batch, int smem_limit, cudaStream_t s,
                     int* m_out = nullptr) {
+    const HanserArgs<T>& a = a_in;
     // largest rows-per-CTA M whose working set allows two CTAs per SM, else the largest that fits
     int pick = 0;
     const int cand[3] = {64, 32, 16};
     static const int forced = [] { const char* e = getenv("PYOTF_B200_K1_ROWS"); return e ? atoi(e) : 0; }();   // tuning knob
-    if (forced && forced <= N && (forced != 16 || N <= 64) && hanser_smem_for<T, N>(forced, a.KP) <= (size_t)smem_limit) pick = forced;
+    if (forced && forced <= N && forced != 128 && (forced != 16 || N <= 64) && hanser_smem_for<T, N>(forced, a.KP) <= (size_t)smem_limit) pick = forced;
     // 64 or 32 rows per CTA, two CTAs per SM if the working set allows, else one; 16 rows only as a last
     // resort (its radix-16 fold spills registers badly: measured 20x slower)
     for (int pass = 0; pass < 3 && !pick; ++pass)
@@ -150,7 +168,25 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a, int tabm, int
             if (need <= lim) pick = M;
         }
     PYOTF_REQUIRE(pick != 0, "hanser_psf: pupil support too large for the fused on-chip path at this size/dtype");
+    // even-symmetric variant: compact work area (the choice above is made on the full pitch, as before)
+    const bool sym = hanser_use_sym(a);
+    HanserArgs<T> as = a;
+    if (sym) as.KP = hanser_sym_pitch(a.f0);
+    if constexpr (N == 256) {
+        // 128 rows per CTA when two such CTAs share an SM and the 64-row grid would not fit one wave anyway
+        const bool fits = sym && HanserSmem<N, 128, T>::bytes(as.KP) <= (size_t)(smem_limit / 2 - 1024);
+        int sms = 0;
+        PYOTF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        const long long ctas64 = (long long)(N / 64) * a.nz * batch;
+        if (fits && (forced == 128 || (!forced && pick == 64 && ctas64 > 2ll * sms))) pick = 128;
+    }
     if (m_out) { *m_out = pick; return 0; }
+    if (pick == 128) { if constexpr (N == 256) return hanser_launch_sym128<T, N>(as, tabm, batch, s); }
+    if (sym) {
+        if (pick == 64) { if constexpr (N >= 64) return hanser_launch_nm<T, N, 64>(h, as, tabm, batch, s); }
+        if (pick == 32) { if constexpr (N >= 32) return hanser_launch_nm<T, N, 32>(h, as, tabm, batch, s); }
+        if constexpr (N <= 64) return hanser_launch_nm<T, N, 16>(h, as, tabm, batch, s);
+    }
     if (pick == 64) { if constexpr (N >= 64) return hanser_launch_nm<T, N, 64>(h, a, tabm, batch, s); }
     if (pick == 32) { if constexpr (N >= 32) return hanser_launch_nm<T, N, 32>(h, a, tabm, batch, s); }
     if constexpr (N <= 64) return hanser_launch_nm<T, N, 16>(h, a, tabm, batch, s);
