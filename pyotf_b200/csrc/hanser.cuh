@@ -369,6 +369,15 @@ __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const 
     }
 }
 
+// Phase timestamps of K1 (debug builds only: -DPYOTF_K1_TIMING, tools/k1_phases.py); compiled out otherwise.
+#ifdef PYOTF_K1_TIMING
+static __device__ unsigned long long g_k1_marks[4096 * 8];
+__device__ __forceinline__ unsigned long long k1_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define K1_MARK(i) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 4096) g_k1_marks[blockIdx.x * 8 + (i)] = ((i) >= 6 ? k1_globaltimer() : (unsigned long long)clock64()); } while (0)
+#else
+#define K1_MARK(i) do { } while (0)
+#endif
+
 // TAB: the defocus factor exp(2 pi i kz z) depends on (|fy|, |fx|) only through fy^2 + fx^2, so
 // when the support box is symmetric each CTA evaluates it once per octant entry (i >= j >= 0)
 // into a shared-memory quadrant table instead of once per pupil pixel (6x fewer sincos for the
@@ -384,6 +393,7 @@ template <typename T, int N, int M, int TABM, bool SYM>
 __global__ void __launch_bounds__(256, (M == 128 ? 2 : 0)) hanser_psf_kernel(HanserArgs<T> a) {
     constexpr bool TAB = TABM != 0;
     static_assert(!SYM || TAB, "the symmetric path needs the (symmetric-box) table");
+    K1_MARK(6); K1_MARK(0);
     pdl_launch_dependents();          // a following K1 launch may be scheduled while this grid drains
     // default: wait for the preceding kernel before reading anything (only the launch latency overlaps);
     // streaming mode: wait only before the first global store (the whole compute phase overlaps)
@@ -434,6 +444,7 @@ __global__ void __launch_bounds__(256, (M == 128 ? 2 : 0)) hanser_psf_kernel(Han
     const bool colactive = rl < nrl && kx < K;
 
     const size_t plane_elems = (size_t)N * N;
+    K1_MARK(1);
 
     for (int v = 0; v < a.nvec; ++v) {
         if constexpr (TABM == 2) {
@@ -453,6 +464,7 @@ __global__ void __launch_bounds__(256, (M == 128 ? 2 : 0)) hanser_psf_kernel(Han
                 __syncthreads();
             }
         }
+        K1_MARK(2);
         // scalar model + ideal pupil: the (radially symmetric) apodisation rides in the defocus table
         const bool tab_only = TAB && a.amp_in_tab;
         const T* __restrict__ amp = a.ampc + (size_t)v * KK;
@@ -465,6 +477,7 @@ __global__ void __launch_bounds__(256, (M == 128 ? 2 : 0)) hanser_psf_kernel(Han
                 else if (TAB && tab_only) hanser_fold_cols<TAB, TAB ? FOLD_TAB_ONLY : FOLD_AMP, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
                 else hanser_fold_cols<TAB, FOLD_AMP, T, N, M>(U, tws, Dq, amp, pupil, kzc, z, K, KP, f0, r, kx, rl, nrl);
             }
+            K1_MARK(3);
             if constexpr (L1 > 1) {
                 __syncthreads();
                 if (colactive) {
@@ -483,6 +496,7 @@ __global__ void __launch_bounds__(256, (M == 128 ? 2 : 0)) hanser_psf_kernel(Han
         // ---------------- rows: FFT_N over kx + epilogue ----------------
         // everything so far read per-handle constants and wrote shared memory only; the stores below must
         // not overtake those of an earlier launch into the same buffers (no-op for ordinary launches)
+        K1_MARK(4);
         if (v == 0 && a.overlap) pdl_wait();
         {
             constexpr int R1 = RP::R1, L1 = RP::R2, G = RP::G, NG = SM::NG, PITCH = SM::PITCH;
@@ -570,6 +584,7 @@ __global__ void __launch_bounds__(256, (M == 128 ? 2 : 0)) hanser_psf_kernel(Han
             }
         }
     }
+    K1_MARK(5); K1_MARK(7);
 }
 
 }  // namespace pyotf

@@ -5,3 +5,9 @@ template int hanser_pack<float>(const pyotf_hanser*, const void*, int, void*, cu
 template int hanser_launch<float>(const pyotf_hanser*, const double*, int, const void*, int, long long, void*, void*,
                                   cudaStream_t);
 }  // namespace pyotf
+
+#ifdef PYOTF_K1_TIMING
+extern "C" int pyotf_b200_debug_k1_marks(unsigned long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, pyotf::g_k1_marks, sizeof(unsigned long long) * n);
+}
+#endif

@@ -141,6 +141,46 @@ def test_streaming_mode_is_bit_identical():
     assert torch.equal(same, ref[-1])
 
 
+def test_rows128_variant_matches_rows64_and_oracle():
+    """Stacks long enough that the 64-row grid would not fit one wave (4 nz > 2 x SMs) run the 128-row CTAs of the
+    even-symmetric variant, also with PSFa kept and in streaming mode: same planes as the short (64-row) stacks
+    within fp32 rounding (different column-FFT factorisation), and within 1e-5 of the oracle."""
+    import torch
+
+    from oracle import pyotf_oracle as orc
+    from pyotf_b200 import _engine as eng
+
+    wl, na, ni, res, size = 520, 0.85, 1.0, 130, 256
+    h = eng.hanser_handle(wl, na, ni, res, size, "none", "sine", "fp32", -1)
+    nz = 160
+    zr = (np.arange(nz) - 77) * 125.0 + 11.0
+    psfa_long, psfi_long = h.psf(eng.to_device_f64(zr), want_psfa=True, want_psfi=True)
+    short_a, short_i = [], []
+    for k in range(0, nz, 40):
+        a, i = h.psf(eng.to_device_f64(zr[k:k + 40]), want_psfa=True, want_psfi=True)
+        short_a.append(a[0].clone()); short_i.append(i[0].clone())
+    h.set_overlap(True)
+    try:
+        stream_i = h.psf(eng.to_device_f64(zr))[1].clone()
+    finally:
+        h.set_overlap(False)
+    torch.cuda.synchronize()
+    assert torch.equal(stream_i, psfi_long)
+    psfi_long, psfa_long = psfi_long[0].cpu().numpy(), psfa_long[0].cpu().numpy()
+    psfi_short = torch.cat(short_i).cpu().numpy()
+    psfa_short = torch.cat(short_a, dim=1).cpu().numpy()
+    assert rel_l2(psfi_long, psfi_short) <= 2e-6
+    assert rel_l2(psfa_long, psfa_short) <= 2e-6
+    # even symmetry of the stored planes (mirror stores of the rows y > N/2)
+    np.testing.assert_array_equal(psfi_long[:, 1:, :], psfi_long[:, :0:-1, :])
+    sel = [0, 1, 77, 78, 121, 159]
+    ref = orc.hanser_psfa(wl, na, ni, res, size, zr[sel])
+    assert rel_l2(psfa_long[:, sel], ref) <= 1e-5
+    assert rel_l2(psfi_long[sel], orc.psfi(ref)) <= 1e-5
+    for j, k in enumerate(sel):                       # worst single plane
+        assert rel_l2(psfi_long[k], orc.psfi(ref)[j]) <= 1e-5
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
 def test_wide_support_high_na(precision):
     """High-NA optics at coarse sampling: the pupil box (K = 149 at 256^2) is too large for the staged defocus
