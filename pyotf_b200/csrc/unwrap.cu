@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -40,14 +41,23 @@ extern "C" int pyotf_b200_unwrap_phase_2d(const double* in, double* out, int ny,
     auto t0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (prof) { auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "unwrap %s: %.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count()); t0 = t1; } };
     std::vector<double> v(n), rel(n);
-    for (int i = 0; i < n; ++i) v[i] = wrap(in[i]);   // already in [-pi, pi] for np.angle output
-    for (int y = 0; y < ny; ++y)
+    // rows that are entirely zero (the region outside the aperture of a retrieved pupil): where three
+    // consecutive rows are, every second difference -- hence the reliability -- is exactly 0
+    std::vector<unsigned char> rowzero(ny);
+    for (int y = 0; y < ny; ++y) {
+        bool z = true;
+        for (int x = 0; x < nx; ++x) { const double w = wrap(in[y * nx + x]); v[y * nx + x] = w; z = z && w == 0.0; }
+        rowzero[y] = z;                                   // (np.angle output is already in [-pi, pi])
+    }
+    for (int y = 0; y < ny; ++y) {
+        const bool flat = y > 0 && y < ny - 1 && rowzero[y - 1] && rowzero[y] && rowzero[y + 1];
         for (int x = 0; x < nx; ++x) {
             const int i = y * nx + x;
             if (y == 0 || x == 0 || y == ny - 1 || x == nx - 1) {
                 rel[i] = 1e7 + (double)((uint32_t)i * 2654435761u >> 8);    // borders last, deterministic order
                 continue;
             }
+            if (flat) { rel[i] = 0.0; continue; }
             const double c = v[i];
             const double H = wrap(v[i - 1] - c) - wrap(c - v[i + 1]);
             const double V = wrap(v[i - nx] - c) - wrap(c - v[i + nx]);
@@ -55,33 +65,60 @@ extern "C" int pyotf_b200_unwrap_phase_2d(const double* in, double* out, int ny,
             const double D2 = wrap(v[i - nx + 1] - c) - wrap(c - v[i + nx - 1]);
             rel[i] = H * H + V * V + D1 * D1 + D2 * D2;
         }
+    }
     lap("reliability");
-    struct Edge { double r; int a, b; };
-    std::vector<Edge> edges;
-    edges.reserve((size_t)2 * n);
-    for (int y = 0; y < ny; ++y)
-        for (int x = 0; x < nx; ++x) {
-            const int i = y * nx + x;
-            if (x + 1 < nx) edges.push_back({rel[i] + rel[i + 1], i, i + 1});
-            if (y + 1 < ny) edges.push_back({rel[i] + rel[i + nx], i, i + nx});
-        }
-    lap("edges");
-    // ascending reliability, ties in generation order.  Most edges of a retrieved pupil lie in the zero
-    // region outside the aperture (reliability exactly 0): they are moved to the front unsorted and only the
-    // rest is sorted -- the same order a stable sort of everything would give.
-    auto mid = std::stable_partition(edges.begin(), edges.end(), [](const Edge& e) { return e.r == 0.0; });
-    std::stable_sort(mid, edges.end(), [](const Edge& p, const Edge& q) { return p.r < q.r; });
-    lap("sort");
     UnionFind uf(n);
-    for (const Edge& e : edges) {
+    auto join = [&](int a, int b) {
         int pa, pb;
-        const int ra = uf.find(e.a, pa), rb = uf.find(e.b, pb);
-        if (ra == rb) continue;
-        const int d = jump(v[e.a], v[e.b]);            // n[b] - n[a] that makes the pair continuous
+        const int ra = uf.find(a, pa), rb = uf.find(b, pb);
+        if (ra == rb) return;
+        const int d = jump(v[a], v[b]);                // n[b] - n[a] that makes the pair continuous
         const int nrb_minus_nra = d + pa - pb;
         if (uf.size[ra] > uf.size[rb]) { uf.parent[rb] = ra; uf.pot[rb] = nrb_minus_nra; uf.size[ra] += uf.size[rb]; }
         else { uf.parent[ra] = rb; uf.pot[ra] = -nrb_minus_nra; uf.size[rb] += uf.size[ra]; }
+    };
+    // Edges are taken in ascending reliability, ties in generation order.  Most edges of a retrieved pupil lie in
+    // the zero region outside the aperture (reliability exactly 0): those come first in that order whatever else
+    // there is, so they are joined right here as they are generated and only the rest is stored and sorted --
+    // the same sequence of joins a stable sort of all edges would give.
+    struct Edge { double r; int a, b; };
+    std::vector<Edge> edges;
+    edges.reserve((size_t)n / 2);
+    for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x) {
+            const int i = y * nx + x;
+            if (x + 1 < nx) { const double r = rel[i] + rel[i + 1]; if (r == 0.0) join(i, i + 1); else edges.push_back({r, i, i + 1}); }
+            if (y + 1 < ny) { const double r = rel[i] + rel[i + nx]; if (r == 0.0) join(i, i + nx); else edges.push_back({r, i, i + nx}); }
+        }
+    lap("edges + zero-reliability joins");
+    // stable LSD radix sort on the bit patterns of the (positive, finite) reliabilities: the order of
+    // std::stable_sort by r at a fraction of its cost; anything else (NaN / inf in the input) takes the comparison sort
+    {
+        bool radix_ok = true;
+        for (const Edge& e : edges) radix_ok = radix_ok && e.r > 0.0 && e.r < 1e300;
+        if (edges.empty()) {
+        } else if (radix_ok) {
+            std::vector<Edge> tmp(edges.size());
+            Edge* src = edges.data();
+            Edge* dst = tmp.data();
+            constexpr int BITS = 11, NB = 1 << BITS;
+            auto key = [](const Edge& e) { uint64_t k; memcpy(&k, &e.r, 8); return k; };
+            for (int shift = 0; shift < 64; shift += BITS) {
+                size_t count[NB] = {};
+                for (size_t i = 0; i < edges.size(); ++i) ++count[(key(src[i]) >> shift) & (NB - 1)];
+                if (count[(key(src[0]) >> shift) & (NB - 1)] == edges.size()) continue;     // digit constant: no-op pass
+                size_t pos = 0;
+                for (int d = 0; d < NB; ++d) { const size_t c = count[d]; count[d] = pos; pos += c; }
+                for (size_t i = 0; i < edges.size(); ++i) dst[count[(key(src[i]) >> shift) & (NB - 1)]++] = src[i];
+                std::swap(src, dst);
+            }
+            if (src != edges.data()) memcpy(edges.data(), src, edges.size() * sizeof(Edge));
+        } else {
+            std::stable_sort(edges.begin(), edges.end(), [](const Edge& p, const Edge& q) { return p.r < q.r; });
+        }
     }
+    lap("sort");
+    for (const Edge& e : edges) join(e.a, e.b);
     lap("union");
     for (int i = 0; i < n; ++i) {
         int acc;
