@@ -390,7 +390,7 @@ __device__ __forceinline__ unsigned long long k1_globaltimer() { unsigned long l
 // only the rows y <= N/2 are transformed, each stored to y and to N - y.  Halves both halves of the work
 // for the reference's default model (HanserPSF with no aberration), bit-identical otherwise.
 template <typename T, int N, int M, int TABM, bool SYM>
-__global__ void __launch_bounds__(256, (M == 128 ? 2 : 0)) hanser_psf_kernel(HanserArgs<T> a) {
+__global__ void __launch_bounds__(256, (M == 128 && sizeof(T) == 4 ? 2 : 0)) hanser_psf_kernel(HanserArgs<T> a) {
     constexpr bool TAB = TABM != 0;
     static_assert(!SYM || TAB, "the symmetric path needs the (symmetric-box) table");
     K1_MARK(6); K1_MARK(0);

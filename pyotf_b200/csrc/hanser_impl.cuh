@@ -173,12 +173,16 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a_in, int tabm, 
     HanserArgs<T> as = a;
     if (sym) as.KP = hanser_sym_pitch(a.f0);
     if constexpr (N == 256) {
-        // 128 rows per CTA when two such CTAs share an SM and the 64-row grid would not fit one wave anyway
-        const bool fits = sym && HanserSmem<N, 128, T>::bytes(as.KP) <= (size_t)(smem_limit / 2 - 1024);
+        // 128 rows per CTA when as many such CTAs share an SM as 64-row ones would (two in fp32 mode, one in fp64
+        // mode) and the 64-row grid would not fit one wave anyway
+        const size_t half = (size_t)(smem_limit / 2 - 1024);
+        const size_t need128 = HanserSmem<N, 128, T>::bytes(as.KP), need64 = HanserSmem<N, 64, T>::bytes(as.KP);
+        const int per_sm64 = need64 <= half ? 2 : 1, per_sm128 = need128 <= half ? 2 : (need128 <= (size_t)smem_limit ? 1 : 0);
+        const bool fits = sym && per_sm128 >= per_sm64;
         int sms = 0;
         PYOTF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
         const long long ctas64 = (long long)(N / 64) * a.nz * batch;
-        if (fits && (forced == 128 || (!forced && pick == 64 && ctas64 > 2ll * sms))) pick = 128;
+        if (fits && (forced == 128 || (!forced && pick == 64 && ctas64 > (long long)per_sm64 * sms))) pick = 128;
     }
     if (m_out) { *m_out = pick; return 0; }
     if (pick == 128) { if constexpr (N == 256) return hanser_launch_sym128<T, N>(as, tabm, batch, s); }

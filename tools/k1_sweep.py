@@ -14,11 +14,12 @@ def main():
 
     from pyotf_b200 import _engine as eng
 
-    prec = "fp32"
+    prec = "fp64" if "--precision=fp64" in sys.argv else "fp32"
+    dt = torch.float64 if prec == "fp64" else torch.float32
     h = eng.hanser_handle(520, 0.85, 1.0, 130, 256, "none", "sine", prec, -1)
     for nz in (37, 74, 111, 128, 148, 222, 296, 592, 1184):
         z = eng.to_device_f64((np.arange(nz) - nz // 2) * 300.0)
-        outs = [torch.empty((1, nz, 256, 256), dtype=torch.float32, device="cuda") for _ in range(max(2, 256 // nz + 1))]
+        outs = [torch.empty((1, nz, 256, 256), dtype=dt, device="cuda") for _ in range(max(2, 256 // nz + 1))]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for i in range(5):
             h.psf(z, psfi_out=outs[i % len(outs)])
