@@ -511,8 +511,20 @@ def run_ours(args):
             with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
                 tj = json.load(f)
             traffic, traffic_note = tj.get(precision), tj.get("_note")
+            winst = tj.get("warp_instructions_" + precision)
         except Exception:
-            pass
+            winst = None
+        # the limit that actually binds K1: warp instructions over the SM sub-partition
+        # schedulers at one issue per cycle, next to the HBM figure the contract asks for
+        binding = None
+        if winst:
+            props = torch.cuda.get_device_properties(torch.cuda.current_device())
+            mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+            min_us = winst / (props.multi_processor_count * 4) / mhz
+            binding = {"kind": "instruction issue", "warp_instructions_per_launch": winst,
+                       "schedulers": props.multi_processor_count * 4, "sm_mhz": mhz, "min_us_at_one_issue_per_cycle": min_us,
+                       "frac": min_us / (ms_per_step * 1e3),
+                       "source": "smsp__inst_executed.sum, ncu --set full (profiles/r1_hot_kernels_ncu.md)"}
         line = {
             "metric": "HanserPSF z-planes/s at 256^2", "value": planes_per_s, "unit": "planes/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -528,6 +540,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "kernel": "hanser_psf_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                         "binding_limit": binding,
                          "streaming_mode": {"ms_per_step": stream_ms, "planes_per_s": nz * world / (stream_ms * 1e-3),
                                             "achieved": alg_bytes / (stream_ms * 1e-3) / 1e9,
                                             "frac": alg_bytes / (stream_ms * 1e-3) / 1e9 / peak,
@@ -538,7 +551,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(nz * N * N * esize), "ms_per_step": 1e3 * e2e_s,
                     "path": "HanserPSF.zrange = host array; HanserPSF.PSFi -> numpy (pinned D2H)",
                     "numa_node_rank0": numa_node},
-            # per step: one hanser_psf_kernel launch (4-CTA clusters build the defocus tables through DSMEM)
+            # per step: one hanser_psf_kernel launch (256 CTAs of 128 rows; every CTA builds its plane's defocus table)
             "gpu_launches": args.steps,
         }
         if others is not None:
