@@ -83,6 +83,17 @@ int pyotf_b200_hanser_psf(const pyotf_hanser_t* h, const double* z_dev, int nz, 
                           int batch, long long pupil_stride, void* psfa_out_dev, void* psfi_out_dev,
                           void* stream);
 
+/* pyotf_b200_hanser_psf with the plane positions given on the HOST, as the reference holds them (HanserPSF.zrange is
+ * a numpy array, otf.py:296-333).  Up to 256 planes of a fused-size handle (32 / 64 / 128 / 256) travel by value in
+ * the kernel arguments: a single-stack ideal-pupil launch then reads nothing but the handle's immutable tables
+ * before its first store, so back-to-back launches overlap (programmatic dependent launch; each still waits for its
+ * predecessor before its first store) with no promise needed from the caller.  Longer stacks and other sizes are
+ * uploaded into a buffer the handle owns (stream-ordered) and take the ordinary path.  z_host may be reused as soon
+ * as the call returns.  Results are bit-identical to pyotf_b200_hanser_psf. */
+int pyotf_b200_hanser_psf_zhost(pyotf_hanser_t* h, const double* z_host, int nz, const void* pupilc_dev,
+                                int batch, long long pupil_stride, void* psfa_out_dev, void* psfi_out_dev,
+                                void* stream);
+
 /* Streaming mode for back-to-back single-stack launches with the ideal pupil.  enable = 1: the caller promises
  * that z_dev is not written by the kernel that precedes a pyotf_b200_hanser_psf call in its stream (uploads by
  * cudaMemcpy are fine).  Consecutive launches then overlap (programmatic dependent launch): the next stack's

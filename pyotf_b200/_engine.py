@@ -99,10 +99,17 @@ class HanserHandle:
         return out
 
     def psf(self, z_dev, pupilc=None, batch=1, want_psfa=False, want_psfi=True, psfa_out=None, psfi_out=None):
-        """Run K1.  Returns (psfa or None, psfi or None) as device tensors."""
+        """Run K1.  Returns (psfa or None, psfi or None) as device tensors.  ``z_dev`` is a float64 device tensor or
+        a host array of plane positions (pyotf_b200_hanser_psf_zhost: short stacks travel in the kernel arguments)."""
         torch = _torch()
         rt, ct = torch_dtypes(self.precision)
-        nz, N = int(z_dev.numel()), self.size
+        z_host = None
+        if not torch.is_tensor(z_dev):
+            z_host = np.ascontiguousarray(np.atleast_1d(np.asarray(z_dev, dtype=np.float64)))
+            nz = int(z_host.size)
+        else:
+            nz = int(z_dev.numel())
+        N = self.size
         stride = 0
         if pupilc is not None:
             if pupilc.dim() == 2:
@@ -114,8 +121,12 @@ class HanserHandle:
             psfa_out = torch.empty((batch, self.nvec, nz, N, N), dtype=ct, device="cuda")
         if want_psfi and psfi_out is None:
             psfi_out = torch.empty((batch, nz, N, N), dtype=rt, device="cuda")
-        _lib.check(_lib.load().pyotf_b200_hanser_psf(
-            self._h, ptr(z_dev), nz, ptr(pupilc), batch, stride, ptr(psfa_out), ptr(psfi_out), stream_ptr()))
+        if z_host is not None:
+            _lib.check(_lib.load().pyotf_b200_hanser_psf_zhost(
+                self._h, z_host.ctypes.data, nz, ptr(pupilc), batch, stride, ptr(psfa_out), ptr(psfi_out), stream_ptr()))
+        else:
+            _lib.check(_lib.load().pyotf_b200_hanser_psf(
+                self._h, ptr(z_dev), nz, ptr(pupilc), batch, stride, ptr(psfa_out), ptr(psfi_out), stream_ptr()))
         return psfa_out, psfi_out
 
 

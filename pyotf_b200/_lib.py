@@ -47,6 +47,7 @@ PROTOTYPES = {
     "pyotf_b200_pupil_support": (_i, [_vp, _i, _ip, _vp]),
     "pyotf_b200_hanser_pack_pupil": (_i, [_vp, _vp, _i, _vp, _vp]),
     "pyotf_b200_hanser_psf": (_i, [_vp, _vp, _i, _vp, _i, _ll, _vp, _vp, _vp]),
+    "pyotf_b200_hanser_psf_zhost": (_i, [_vp, _vp, _i, _vp, _i, _ll, _vp, _vp, _vp]),
     "pyotf_b200_hanser_kspace": (_i, [_d, _d, _d, _i, _vp, _vp, _vp, _vp]),
     "pyotf_b200_hanser_defocus": (_i, [_vp, _ll, _vp, _i, _vp, _vp]),
     "pyotf_b200_zernike": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _vp, _vp]),

@@ -117,13 +117,17 @@ int pyotf_b200_hanser_create(const pyotf_hanser_params* p, void* stream, pyotf_h
     PYOTF_CUDA_OK(cudaMalloc(&h->tw, (size_t)h->N * 2 * es));
     int rc = p->dtype == PYOTF_F32 ? hanser_build_tables<float>(h, s) : hanser_build_tables<double>(h, s);
     if (rc) { pyotf_b200_hanser_destroy(h); return rc; }
+    // the tables are immutable from here on and visible to every later launch, including launches that read them
+    // before waiting for their predecessor in the stream (programmatic dependent launch)
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error(std::string("hanser_create: ") + cudaGetErrorString(e)); pyotf_b200_hanser_destroy(h); return 2; }
     *out = h;
     return 0;
 }
 
 int pyotf_b200_hanser_destroy(pyotf_hanser_t* h) {
     if (!h) return 0;
-    cudaFree(h->kzc); cudaFree(h->ampc); cudaFree(h->maskc); cudaFree(h->tw); cudaFree(h->dtab); cudaFree(h->octkz); cudaFree(h->octamp); cudaFree(h->octij); cudaFree(h->pscratch);
+    cudaFree(h->kzc); cudaFree(h->ampc); cudaFree(h->maskc); cudaFree(h->tw); cudaFree(h->dtab); cudaFree(h->octkz); cudaFree(h->octamp); cudaFree(h->octij); cudaFree(h->pscratch); cudaFree(h->zbuf);
     delete h;
     return 0;
 }
@@ -189,6 +193,20 @@ int pyotf_b200_hanser_psf(const pyotf_hanser_t* h, const double* z_dev, int nz, 
     return h->p.dtype == PYOTF_F32
                ? hanser_launch<float>(h, z_dev, nz, pupilc_dev, batch, pupil_stride, psfa_out_dev, psfi_out_dev, s)
                : hanser_launch<double>(h, z_dev, nz, pupilc_dev, batch, pupil_stride, psfa_out_dev, psfi_out_dev, s);
+}
+
+int pyotf_b200_hanser_psf_zhost(pyotf_hanser_t* h, const double* z_host, int nz, const void* pupilc_dev, int batch,
+                                long long pupil_stride, void* psfa_out_dev, void* psfi_out_dev, void* stream) {
+    PYOTF_REQUIRE(h && z_host, "hanser_psf_zhost: null argument");
+    PYOTF_REQUIRE(nz > 0 && batch > 0, "hanser_psf_zhost: nz and batch must be positive");
+    PYOTF_REQUIRE(psfa_out_dev || psfi_out_dev, "hanser_psf_zhost: no output requested");
+    PYOTF_REQUIRE((h->p.support == -1) == (pupilc_dev == nullptr),
+                  "hanser_psf_zhost: handle support mode and pupil argument disagree");
+    PYOTF_REQUIRE(batch <= 65535, "hanser_psf_zhost: batch too large for one launch");
+    cudaStream_t s = (cudaStream_t)stream;
+    return h->p.dtype == PYOTF_F32
+               ? hanser_launch<float>(h, nullptr, nz, pupilc_dev, batch, pupil_stride, psfa_out_dev, psfi_out_dev, s, z_host)
+               : hanser_launch<double>(h, nullptr, nz, pupilc_dev, batch, pupil_stride, psfa_out_dev, psfi_out_dev, s, z_host);
 }
 
 int pyotf_b200_hanser_kspace(double wl, double ni, double res, int size, double* kr, double* phi, double* kz,

@@ -68,6 +68,8 @@ struct pyotf_hanser {
     int overlap = 0;                // streaming mode (pyotf_b200_hanser_set_overlap)
     void* pscratch = nullptr;       // pupil * amp of the last launch (scalar model), grown on demand
     size_t pscratch_cap = 0;
+    double* zbuf = nullptr;         // plane positions uploaded by pyotf_b200_hanser_psf_zhost (stacks too long for the kernel arguments)
+    size_t zbuf_cap = 0;
 };
 
 struct pyotf_comm;
@@ -109,7 +111,7 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
 template <typename T> int hanser_build_tables(pyotf_hanser* h, cudaStream_t s);
 template <typename T>
 int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pupilc, int batch,
-                  long long pupil_stride, void* psfa, void* psfi, cudaStream_t s);
+                  long long pupil_stride, void* psfa, void* psfi, cudaStream_t s, const double* z_host = nullptr);
 template <typename T>
 int hanser_pack(const pyotf_hanser* h, const void* src, int batch, void* dst, cudaStream_t s);
 template <typename T>

@@ -142,6 +142,9 @@ static __global__ void pupil_support_kernel(int N, const double2* __restrict__ s
     if ((threadIdx.x & 31) == 0 && h > 0) atomicMax(hmax, h);
 }
 
+// plane positions that travel by value in the kernel arguments (pyotf_b200_hanser_psf_zhost)
+#define PYOTF_Z_PARAM_MAX 256
+
 template <typename T> struct HanserArgs {
     const double* kzc;        // [KR][K]   kz in cycles per length unit (rows >= K are zero)
     const T* ampc;            // [nvec][KR][K]
@@ -159,6 +162,8 @@ template <typename T> struct HanserArgs {
     cplx<T>* psfa;            // [B][nvec][nz][N][N] or nullptr
     int K, KR, KP, f0, nz, nvec;
     long long pupil_stride;   // elements between pupils in pupilc (0 = shared)
+    int z_in_params;          // plane positions are in zv (host-side zrange, <= PYOTF_Z_PARAM_MAX planes), z unused
+    double zv[PYOTF_Z_PARAM_MAX];
 };
 
 template <int N, int M, typename T, int NTHREADS = 256> struct HanserSmem {
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(256, (M == 128 && sizeof(T) == 4 ? 2 : 0)) han
     // lookups are shared-memory hits instead of L2 round trips
     cplx<T>* Dq = EX;
     const int K = a.K, KP = a.KP, f0 = a.f0, KK = a.KR * K;
-    const double z = a.z[plane];
+    const double z = a.z_in_params ? a.zv[plane] : a.z[plane];
     const cplx<T>* __restrict__ pupil = a.pupilc ? a.pupilc + (size_t)bidx * a.pupil_stride : nullptr;
     const double* __restrict__ kzc = a.kzc;
 

@@ -3,7 +3,7 @@ namespace pyotf {
 template int hanser_build_tables<float>(pyotf_hanser*, cudaStream_t);
 template int hanser_pack<float>(const pyotf_hanser*, const void*, int, void*, cudaStream_t);
 template int hanser_launch<float>(const pyotf_hanser*, const double*, int, const void*, int, long long, void*, void*,
-                                  cudaStream_t);
+                                  cudaStream_t, const double*);
 }  // namespace pyotf
 
 #ifdef PYOTF_K1_TIMING

@@ -3,5 +3,5 @@ namespace pyotf {
 template int hanser_build_tables<double>(pyotf_hanser*, cudaStream_t);
 template int hanser_pack<double>(const pyotf_hanser*, const void*, int, void*, cudaStream_t);
 template int hanser_launch<double>(const pyotf_hanser*, const double*, int, const void*, int, long long, void*, void*,
-                                  cudaStream_t);
+                                  cudaStream_t, const double*);
 }  // namespace pyotf

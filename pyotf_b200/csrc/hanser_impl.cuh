@@ -275,12 +275,38 @@ int hanser_launch_big(const pyotf_hanser* h, const double* z, int nz, const void
 
 template <typename T>
 int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pupilc, int batch,
-                  long long pupil_stride, void* psfa, void* psfi, cudaStream_t s) {
+                  long long pupil_stride, void* psfa, void* psfi, cudaStream_t s, const double* z_host) {
     HanserArgs<T> a;
+    a.z_in_params = 0;
+    const bool fused_n = h->N == 32 || h->N == 64 || h->N == 128 || h->N == 256;
+    // host-side zrange: short stacks of the fused path travel in the kernel arguments, anything else is uploaded
+    // into a buffer the handle owns (stream-ordered: the copy queues behind the previous launch that reads it)
+    const bool zparams = z_host && nz <= PYOTF_Z_PARAM_MAX && fused_n;
+    auto upload_z = [&]() -> int {
+        pyotf_hanser* hm = const_cast<pyotf_hanser*>(h);
+        const size_t need = sizeof(double) * (size_t)nz;
+        if (need > hm->zbuf_cap) {
+            PYOTF_CUDA_OK(cudaStreamSynchronize(s));
+            cudaFree(hm->zbuf); hm->zbuf = nullptr; hm->zbuf_cap = 0;
+            PYOTF_CUDA_OK(cudaMalloc(&hm->zbuf, need));
+            hm->zbuf_cap = need;
+        }
+        PYOTF_CUDA_OK(cudaMemcpyAsync(hm->zbuf, z_host, need, cudaMemcpyHostToDevice, s));
+        z = hm->zbuf;
+        return 0;
+    };
+    if (z_host && !zparams) { if (int rc = upload_z()) return rc; }
+    if (zparams) {
+        for (int i = 0; i < nz; ++i) a.zv[i] = z_host[i];
+        a.z_in_params = 1;
+    }
     a.kzc = h->kzc; a.ampc = (const T*)h->ampc; a.pupilc = (const cplx<T>*)pupilc;
     a.tw = (const cplx<T>*)h->tw; a.z = z; a.psfi = (T*)psfi; a.psfa = (cplx<T>*)psfa;
     a.K = h->K; a.KR = h->KR; a.KP = h->KP; a.f0 = h->f0; a.nz = nz; a.nvec = h->nvec; a.pupil_stride = pupil_stride;
-    a.overlap = h->overlap;
+    // z by value: the launch reads nothing but the handle's immutable tables before its first store, so
+    // back-to-back single stacks may overlap without any promise from the caller (only the PDL launch path of
+    // hanser_launch_nmt looks at this flag)
+    a.overlap = (h->overlap || zparams) ? 1 : 0;
     int smem_limit = 0;
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     a.pupil_has_amp = 0;
@@ -342,6 +368,7 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
                 PYOTF_CUDA_OK(cudaMalloc(&hm->dtab, need));
                 hm->dtab_cap = need;
             }
+            if (zparams) { if (int rcz = upload_z()) return rcz; a.z = z; }   // the table kernel reads z from memory
             rc = hanser_build_dtabs<T>(h, z, nz, a.amp_in_tab != 0, (cplx<T>*)hm->dtab, s);
             if (rc) return rc;
             a.dtab = (const cplx<T>*)hm->dtab;

@@ -326,8 +326,8 @@ class HanserPSF(BasePSF):
 
     def _run(self, pupil_base, want_psfa, want_psfi):
         h, pupilc = self._handle_and_pupil(pupil_base)
-        z = _engine.to_device_f64(self.zrange)
-        psfa, psfi = h.psf(z, pupilc, want_psfa=want_psfa, want_psfi=want_psfi)
+        # zrange stays on the host, as in the reference: pyotf_b200_hanser_psf_zhost
+        psfa, psfi = h.psf(np.asarray(self.zrange, dtype=np.float64), pupilc, want_psfa=want_psfa, want_psfi=want_psfi)
         return (psfa[0] if psfa is not None else None), (psfi[0] if psfi is not None else None)
 
     def _gen_psf(self, pupil_base=None):

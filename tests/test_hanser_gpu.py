@@ -141,6 +141,49 @@ def test_streaming_mode_is_bit_identical():
     assert torch.equal(same, ref[-1])
 
 
+def test_host_zrange_entry_is_bit_identical():
+    """pyotf_b200_hanser_psf_zhost (zrange on the host, as the reference holds it): short stacks travel in the kernel
+    arguments and overlap back to back, long stacks / user pupils / vectorial models / other sizes are uploaded;
+    every variant equals the device-z entry bit for bit, also for repeated launches into one buffer."""
+    import torch
+
+    from pyotf_b200 import _engine as eng
+
+    h = eng.hanser_handle(520, 0.85, 1.0, 130, 256, "none", "sine", "fp32", -1)
+    zs = [(np.arange(nz) - nz // 2 + 3 * k) * 150.0 + 7.0 for k, nz in enumerate((1, 40, 128, 256, 257, 300))]
+    ref = [h.psf(eng.to_device_f64(z))[1].clone() for z in zs]
+    torch.cuda.synchronize()
+    got = [h.psf(z)[1] for z in zs]                       # numpy in -> zhost entry
+    same = torch.empty_like(ref[2])
+    for k in range(6):                                    # six overlapping launches into ONE buffer
+        h.psf(zs[2] + 10.0 * k, psfi_out=same)
+    last = h.psf(eng.to_device_f64(zs[2] + 50.0))[1]
+    torch.cuda.synchronize()
+    for k in range(len(zs)):
+        assert torch.equal(got[k], ref[k]), k
+    assert torch.equal(same, last)
+    # fp64, vectorial model, PSFa kept
+    h6 = eng.hanser_handle(520, 0.85, 1.0, 130, 64, "total", "herschel", "fp64", -1)
+    z = np.array([-500.0, 0.0, 125.0])
+    a0, i0 = h6.psf(eng.to_device_f64(z), want_psfa=True)
+    a1, i1 = h6.psf(z, want_psfa=True)
+    assert torch.equal(a0, a1) and torch.equal(i0, i1)
+    # user pupil (precomputed-table path) and a size outside the fused kernel's set (two-pass path)
+    rng = np.random.default_rng(3)
+    for size in (128, 96):
+        pupil = np.zeros((size, size), complex)
+        f = np.fft.fftfreq(size, 1.0 / size)
+        m = np.hypot(*np.meshgrid(f, f)) <= 20
+        pupil[m] = np.exp(1j * rng.standard_normal(int(m.sum())))
+        pd = eng.to_device_c128(pupil)
+        hp = eng.hanser_handle(520, 0.85, 1.0, 130, size, "none", "sine", "fp32", eng.pupil_support(pd))
+        pc = hp.pack_pupil(pd[None])
+        z = np.linspace(-900, 900, 7)
+        i0 = hp.psf(eng.to_device_f64(z), pc)[1]
+        i1 = hp.psf(z, pc)[1]
+        assert torch.equal(i0, i1), size
+
+
 def test_rows128_variant_matches_rows64_and_oracle():
     """Stacks long enough that the 64-row grid would not fit one wave (4 nz > 2 x SMs) run the 128-row CTAs of the
     even-symmetric variant, also with PSFa kept and in streaming mode: same planes as the short (64-row) stacks
