@@ -362,8 +362,10 @@ __device__ __forceinline__ void hanser_fold_cols(cplx<T>* __restrict__ U, const 
             }
         }
         if constexpr (R > 1) {
+            if (r != 0) {                                         // CTA-uniform; w^0 = 1 for the residue-0 CTA
 #pragma unroll
-            for (int u = 0; u < Q1; ++u) xs[u] = cmul(xs[u], tws[((bp + L1 * (m0 + u)) * r) & (N - 1)]);
+                for (int u = 0; u < Q1; ++u) xs[u] = cmul(xs[u], tws[((bp + L1 * (m0 + u)) * r) & (N - 1)]);
+            }
         }
         fft_radix<1, Q1>(xs);
 #pragma unroll
