@@ -166,6 +166,25 @@ template <int DIR, typename T> __device__ __forceinline__ void fft16(cplx<T>* x)
     }
 }
 
+// radix-16 whose inputs x[4] .. x[11] are known to be zero (band-limited rows: the support box covers less than
+// half of the frequencies); the first-stage radix-4 butterflies collapse to two inputs.  x[4..11] are not read.
+template <int DIR, typename T> __device__ __forceinline__ void fft16_mid0(cplx<T>* x) {
+    cplx<T> t[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const cplx<T> a = x[b], d = x[12 + b], id = mul_i<DIR>(d);
+        t[b][0] = a + d; t[b][1] = a - id; t[b][2] = a - d; t[b][3] = a + id;
+    }
+    t[1][1] = mul_w16<DIR, 1>(t[1][1]); t[1][2] = mul_w16<DIR, 2>(t[1][2]); t[1][3] = mul_w16<DIR, 3>(t[1][3]);
+    t[2][1] = mul_w16<DIR, 2>(t[2][1]); t[2][2] = mul_w16<DIR, 4>(t[2][2]); t[2][3] = mul_w16<DIR, 6>(t[2][3]);
+    t[3][1] = mul_w16<DIR, 3>(t[3][1]); t[3][2] = mul_w16<DIR, 6>(t[3][2]); t[3][3] = mul_w16<DIR, 9>(t[3][3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        fft4<DIR>(t[0][c], t[1][c], t[2][c], t[3][c]);
+        x[c] = t[0][c]; x[c + 4] = t[1][c]; x[c + 8] = t[2][c]; x[c + 12] = t[3][c];
+    }
+}
+
 template <int DIR, int R, typename T> __device__ __forceinline__ void fft_radix(cplx<T>* x) {
     static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "radix");
     if constexpr (R == 2) fft2<DIR>(x[0], x[1]);

@@ -531,8 +531,12 @@ __global__ void __launch_bounds__(256, (M == 128 && sizeof(T) == 4 ? 2 : 0)) han
                 const int ysm = (ym + N / 2) & (N - 1);
                 const cplx<T>* Ul = U + (size_t)l * KP;
                 cplx<T> x[R1];
+                // band-limited rows: a support box narrower than N/2 leaves the middle half of the frequencies
+                // (k = L1*q + g with R1/4 <= q < 3 R1/4) empty, and the first radix-16 collapses (CTA-uniform)
+                const bool narrow = R1 == 16 && -f0 < N / 4 && K + f0 <= N / 4;
 #pragma unroll
                 for (int q = 0; q < R1; ++q) {
+                    if (R1 == 16 && narrow && q >= R1 / 4 && q < 3 * R1 / 4) continue;
                     // k = L1*q + g ; positive half k < N/2, else frequency k - N
                     if (L1 * q < N / 2) x[q] = (ipos + L1 * q < K) ? Ul[ipos + L1 * q] : mk<T>(0, 0);
                     else if constexpr (SYM) {                        // column |k - N| = N - k
@@ -541,7 +545,11 @@ __global__ void __launch_bounds__(256, (M == 128 && sizeof(T) == 4 ? 2 : 0)) han
                     }
                     else x[q] = (ineg + L1 * q >= 0) ? Ul[ineg + L1 * q] : mk<T>(0, 0);
                 }
-                fft_radix<1, R1>(x);
+                if constexpr (R1 == 16) {
+                    if (narrow) fft16_mid0<1>(x); else fft_radix<1, R1>(x);
+                } else {
+                    fft_radix<1, R1>(x);
+                }
                 __syncwarp();
 #pragma unroll
                 for (int c = 0; c < R1; ++c) ex[c * PITCH + g] = cmul(x[c], twr[c]);
