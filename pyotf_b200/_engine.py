@@ -27,11 +27,18 @@ def get_precision():
     return _default_precision
 
 
+_cuda_checked = False
+
+
 def _torch():
+    """torch, after checking once that a CUDA device is there (every launch path calls this several times)."""
+    global _cuda_checked
     import torch
 
-    if not torch.cuda.is_available():
-        raise _lib.Pyotf_b200Error("pyotf_b200 needs a CUDA device (B200); there is no CPU fallback")
+    if not _cuda_checked:
+        if not torch.cuda.is_available():
+            raise _lib.Pyotf_b200Error("pyotf_b200 needs a CUDA device (B200); there is no CPU fallback")
+        _cuda_checked = True
     return torch
 
 
