@@ -60,7 +60,35 @@ __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nline
             return;
         }
     }
-    if (LINE_MAJOR) {
+    // full power-of-two tiles: a thread issues a batch of its loads before the first shared-memory store of the
+    // batch (the element loads are generic-pointer loads the compiler will not move across shared stores), so up
+    // to UB requests per thread are in flight instead of one -- the passes are bound by memory-level parallelism
+    constexpr bool FAST = POW2 && (TI * (POW2 ? L : 1)) % 256 == 0;
+    bool fast = false;
+    if constexpr (FAST) fast = nlines == TI && blockDim.x == 256;
+    if constexpr (FAST) {
+        if (fast) {
+            constexpr int PER = TI * L / 256, UB = PER < F::LOAD_BATCH ? PER : F::LOAD_BATCH;
+            static_assert(PER % UB == 0, "load batch must divide the per-thread element count");
+            for (int k0 = 0; k0 < PER; k0 += UB) {
+                cplx<T> v[UB];
+#pragma unroll
+                for (int k = 0; k < UB; ++k) {
+                    const int w = threadIdx.x + 256 * (k0 + k);
+                    const int t = LINE_MAJOR ? w / L : w % TI, l = LINE_MAJOR ? w % L : w / TI;
+                    v[k] = f.load(sline[t], l);
+                }
+#pragma unroll
+                for (int k = 0; k < UB; ++k) {
+                    const int w = threadIdx.x + 256 * (k0 + k);
+                    const int t = LINE_MAJOR ? w / L : w % TI, l = LINE_MAJOR ? w % L : w / TI;
+                    tile[(size_t)t * pitch + fft_pad<POW2>(l)] = v[k];
+                }
+            }
+        }
+    }
+    if (fast) {
+    } else if (LINE_MAJOR) {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {
             int t = w / Lr, l = w - t * Lr;
             tile[(size_t)t * pitch + fft_pad<POW2>(l)] = f.load(sline[t], l);
@@ -126,6 +154,7 @@ __global__ void __launch_bounds__(256) fft_lines_kernel(int Lrt, long long nline
 
 // functors without a reduction / early exit
 struct NoAcc {
+    static constexpr int LOAD_BATCH = 8;              // element loads a thread keeps in flight (power of two)
     static constexpr bool HAS_EMPTY = false;          // functors that can prove a line is all-zero override this
     using Acc = int;
     __device__ __forceinline__ static Acc acc_init() { return 0; }

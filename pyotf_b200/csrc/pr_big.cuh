@@ -36,6 +36,7 @@ struct PrSkip {
 template <typename T> struct PrColInv {
     struct Line { const cplx<T>* w; const T* drow; cplx<T>* p; };
     using Acc = double;
+    static constexpr int LOAD_BATCH = 8;
     static constexpr bool HAS_EMPTY = false;
     PrBigArgs<T> a;
     __device__ __forceinline__ static Acc acc_init() { return 0.0; }
