@@ -56,7 +56,8 @@ def build(force=False, verbose=False):
         cmd = [nvcc(), *ARCH, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OBJ, src[:-3] + ".ptxas.log")
-        open(log, "w").write(r.stderr)
+        # register / spill report of every kernel (kept in the tree as evidence); compile times would churn the file
+        open(log, "w").write("".join(l for l in r.stderr.splitlines(True) if "Compile time" not in l))
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stderr[-4000:]}")
         return obj
