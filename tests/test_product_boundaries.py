@@ -109,3 +109,29 @@ def test_host_unwrap_and_shard_bounds():
         sizes = [hi - lo for lo, hi in b]
         assert max(sizes) - min(sizes) <= 1
         assert sizes == [len(c) for c in np.array_split(np.arange(n), w)]
+
+
+def test_host_unwrap_matches_plain_restatement():
+    """The optimised host unwrap (zero-reliability edges joined as they are generated, all-zero row bands skipped,
+    radix sort) against the plain all-edges / stable-sort / union-find restatement in oracle/unwrap_oracle.py:
+    identical arrays on pupil-like (zero outside an aperture), dense, noisy, flat and tiny inputs."""
+    from oracle import unwrap_oracle as uo
+    from pyotf_b200.phaseretrieval import unwrap_phase
+
+    rng = np.random.default_rng(5)
+    y, x = np.mgrid[-1:1:40j, -1:1:47j]
+    smooth = 9 * (x**2 + y**2) - 5 * x * y
+    inside = x**2 + y**2 < 0.55
+    cases = {
+        "pupil": np.where(inside, np.angle(np.exp(1j * smooth)), 0.0),
+        "noisy pupil": np.where(inside, np.angle(np.exp(1j * (smooth + 0.9 * rng.standard_normal(x.shape)))), 0.0),
+        "dense": np.angle(np.exp(1j * smooth)),
+        "noise": rng.uniform(-np.pi, np.pi, (23, 31)),
+        "flat blocks": np.where((x > 0.3) & (y < 0.5), 1.0, 0.0) + np.where(x < -0.6, 2.5, 0.0),
+        "zeros": np.zeros((9, 12)),
+        "tiny": rng.uniform(-3, 3, (3, 5)),
+        "one row": rng.uniform(-3, 3, (1, 7)),
+        "one pixel": np.ones((1, 1)),
+    }
+    for name, a in cases.items():
+        np.testing.assert_array_equal(unwrap_phase(a), uo.unwrap_phase_2d(a), err_msg=name)
