@@ -20,7 +20,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libpyotf_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-         "-Xptxas", "-v"]
+         "-Xptxas", "-v"] + os.environ.get("PYOTF_B200_BUILD_DEFS", "").split()   # e.g. -DPYOTF_K1_TIMING (debug marks)
 
 
 def nvcc():

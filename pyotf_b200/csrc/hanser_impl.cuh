@@ -198,6 +198,10 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a_in, int tabm, 
     return 1;
 }
 
+// K1s (hanser_sym.cuh, its own translation units hanser_sym_f32.cu / _f64.cu): one CTA per plane, scalar model with
+// the ideal pupil at N = 256, PSFi only.  *done stays false when the configuration does not fit (caller falls back).
+template <typename T> int hanser_sym_launch(const HanserArgs<T>& a, int batch, int smem_limit, cudaStream_t s, bool* done);
+
 // ---------------------------------------------------------------------------------------
 // K1b launchers (hanser_big.cuh): any size, two line-FFT passes per plane chunk
 // ---------------------------------------------------------------------------------------
@@ -372,6 +376,15 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
             rc = hanser_build_dtabs<T>(h, z, nz, a.amp_in_tab != 0, (cplx<T>*)hm->dtab, s);
             if (rc) return rc;
             a.dtab = (const cplx<T>*)hm->dtab;
+        }
+    }
+    if (h->N == 256 && tabm == 3 && a.amp_in_tab && !psfa && psfi && -h->f0 <= 63 && h->octkz && hanser_use_sym(a)) {
+        // the reference's default model: whole-plane CTAs exploiting the even / transpose symmetry (hanser_sym.cuh)
+        static const bool old_sym = getenv("PYOTF_B200_K1_SYM_OLD") != nullptr;
+        if (!old_sym) {
+            bool done = false;
+            int rc = hanser_sym_launch<T>(a, batch, smem_limit, s, &done);
+            if (rc || done) return rc;
         }
     }
     switch (h->N) {

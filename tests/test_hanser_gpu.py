@@ -204,11 +204,15 @@ def test_rows128_variant_matches_rows64_and_oracle():
         short_a.append(a[0].clone()); short_i.append(i[0].clone())
     h.set_overlap(True)
     try:
-        stream_i = h.psf(eng.to_device_f64(zr))[1].clone()
+        stream_a, stream_i = h.psf(eng.to_device_f64(zr), want_psfa=True, want_psfi=True)
+        stream_i = stream_i.clone()
     finally:
         h.set_overlap(False)
     torch.cuda.synchronize()
     assert torch.equal(stream_i, psfi_long)
+    # PSFi alone goes through the whole-plane kernel (hanser_sym.cuh): same planes within fp32 rounding
+    whole_i = h.psf(eng.to_device_f64(zr))[1]
+    assert rel_l2(whole_i[0].cpu().numpy(), psfi_long[0].cpu().numpy()) <= 2e-6
     psfi_long, psfa_long = psfi_long[0].cpu().numpy(), psfa_long[0].cpu().numpy()
     psfi_short = torch.cat(short_i).cpu().numpy()
     psfa_short = torch.cat(short_a, dim=1).cpu().numpy()
@@ -248,3 +252,55 @@ def test_wide_support_high_na(precision):
     r = retrieve_phase(data, dict(wl=wl, na=na, ni=ni, res=res, zrange=z + 33.0), 6, 0, 0, precision=precision)
     assert rel_l2(r.mse, o["mse"]) <= TOL[precision]
     assert rel_l2(r.pupil, o["pupil"]) <= (1e-11 if precision == "fp64" else 2e-5)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_whole_plane_kernel_cfg1_and_overlapping_launches(precision):
+    """K1s (hanser_sym.cuh: one CTA per plane, even / transpose symmetry, PSFi of the default model at 256^2):
+    the full BASELINE config-1 stack against the oracle, exact mirror symmetry of the stored planes, and
+    back-to-back launches -- into rotating buffers (they overlap: each only has to finish after its predecessor)
+    and into one buffer (each waits before its first store) -- bit-identical to serialised launches."""
+    import torch
+
+    from oracle import pyotf_oracle as orc
+    from pyotf_b200 import _engine as eng
+
+    wl, na, ni, res, size, nz = 520, 0.85, 1.0, 130, 256, 128
+    z = orc.default_zrange(nz, 300)
+    h = eng.hanser_handle(wl, na, ni, res, size, "none", "sine", precision, -1)
+    got = h.psf(z)[1]
+    torch.cuda.synchronize()
+    p = got[0].cpu().numpy()
+    ref = orc.psfi(orc.hanser_psfa(wl, na, ni, res, size, z))
+    assert rel_l2(p, ref) <= TOL[precision]
+    assert max(rel_l2(p[i], ref[i]) for i in range(nz)) <= TOL[precision]
+    np.testing.assert_array_equal(p[:, 1:, :], p[:, :0:-1, :])          # y <-> -y
+    np.testing.assert_array_equal(p[:, :, 1:], p[:, :, :0:-1])          # x <-> -x
+    # row 0 (y = -128) is stored from the transposed column x = -128
+    np.testing.assert_array_equal(p[:, 0, :], p[:, :, 0])
+    # different stacks back to back: rotating outputs (no wait before the stores) and a single output buffer
+    stacks = [z + 37.0 * k for k in range(12)]
+    serial = []
+    for zz in stacks:
+        serial.append(h.psf(zz)[1].clone())
+        torch.cuda.synchronize()
+    ring = [torch.empty_like(got) for _ in range(5)]
+    keep = []
+    for k, zz in enumerate(stacks):
+        h.psf(zz, psfi_out=ring[k % 5])
+        if k % 5 == 4 or k == len(stacks) - 1:
+            torch.cuda.synchronize()
+            for j in range(k - k % 5, k + 1):
+                keep.append(ring[j % 5].clone())
+    for a, b in zip(keep, serial):
+        assert torch.equal(a, b)
+    one = torch.empty_like(got)
+    for zz in stacks:
+        h.psf(zz, psfi_out=one)
+    torch.cuda.synchronize()
+    assert torch.equal(one, serial[-1])
+    # odd plane counts, planes far from focus, a device-resident z (the launch then waits for its predecessor first)
+    z2 = np.array([-20000.0, -1234.5, 0.0, 17.0, 5000.0])
+    r2 = orc.psfi(orc.hanser_psfa(wl, na, ni, res, size, z2))
+    assert rel_l2(h.psf(z2)[1][0].cpu().numpy(), r2) <= TOL[precision]
+    assert rel_l2(h.psf(eng.to_device_f64(z2))[1][0].cpu().numpy(), r2) <= TOL[precision]
