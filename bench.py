@@ -25,6 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG1 = dict(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=256, zsize=128)
+# identical in both arms' config.workload (the driver compares the strings)
+WORKLOAD = ("hanser256: HanserPSF(wl=520,na=0.85,ni=1.0,res=130,zres=300,size=256,zsize=128) -> PSFi "
+            "(BASELINE config 1)")
 
 
 def measured_peaks():
@@ -144,8 +147,8 @@ def run_reference(args):
         "impl": "reference", "metric": "HanserPSF z-planes/s at 256^2", "value": value, "unit": "planes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "hanser256: HanserPSF 256^2 x 128 planes (BASELINE config 1) -> PSFi, CPU",
-                   "step": "one 128-plane stack, z-chunked over a process pool"},
+        "config": {"workload": WORKLOAD,
+                   "step": "one 128-plane stack on the host cores, z-chunked over a process pool (numpy complex128)"},
         "cpu_baseline": {"value": value, "unit": "planes/s", "cores": len(chunks), "kind": "port",
                          "sample": f"oracle port (numpy complex128), full cfg1 stack per step over {len(chunks)} "
                                    f"processes"},
@@ -181,7 +184,7 @@ def cpu_baseline_pr(iters=8):
                       f"in {dt:.1f} s (numpy/pocketfft complex128, 1 of {os.cpu_count()} cores)"}
 
 
-def bench_pr(precision, rank, world, dist, reps=5, iters=100):
+def bench_pr(precision, rank, world, dist, reps=5, iters=100, extras=True):
     """Phase-retrieval iterations/s on BASELINE config 2 (fixture stack, 100 iterations, tolerances 0 so
     that exactly 100 run).  With N ranks the 25 planes are z-sharded (strong scaling) and every iteration
     all-reduces the partial pupil sums over NCCL."""
@@ -244,6 +247,10 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100):
         t0 = time.perf_counter()
         r = retrieve_phase(data, dict(params), iters, 0, 0, precision=precision)
         dt_s = time.perf_counter() - t0
+        out["e2e"] = {"iters_per_s": iters / dt_s, "ms_total": 1e3 * dt_s, "h2d_bytes": int(data.nbytes),
+                      "d2h_bytes": int(r.pupil.nbytes + 3 * 8 * iters),
+                      "path": "retrieve_phase(host ndarray) -> PhaseRetrievalResult incl. host unwrap"}
+    if world == 1 and extras:
         # the same from the raw camera stack (uint16): background removal / clip on the device (N3), then the loop
         from pyotf_b200.utils import prep_data_for_PR, prep_data_for_PR_dev
 
@@ -258,10 +265,7 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100):
         out["e2e_from_raw_u16"] = {"iters_per_s": iters / dt_raw, "ms_total": 1e3 * dt_raw, "h2d_bytes": int(raw.nbytes),
                                    "host_prep_ms_for_comparison": 1e3 * dt_prep_cpu,
                                    "path": "prep_data_for_PR_dev(uint16 stack) -> retrieve_phase(device tensor)"}
-        out["e2e"] = {"iters_per_s": iters / dt_s, "ms_total": 1e3 * dt_s, "h2d_bytes": int(data.nbytes),
-                      "d2h_bytes": int(r.pupil.nbytes + 3 * 8 * iters),
-                      "path": "retrieve_phase(host ndarray) -> PhaseRetrievalResult incl. host unwrap"}
-    if world > 1:
+    if world > 1 and extras:
         # replicas: every rank retrieves the full stack on its own GPU at the same time (no collective) --
         # the batched-independent-retrievals mode SURVEY.md section 8e recommends for short stacks
         dfull = torch.as_tensor(np.ascontiguousarray(data.astype(dt)), device="cuda")
@@ -381,41 +385,45 @@ def bench_other_configs(precision, rank, world):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
+def k1_traffic(precision):
+    """DRAM bytes and warp instructions per K1 launch from the committed ncu capture -- only if that capture was
+    taken from the kernel sources this run uses (tools/ncu_traffic.py stamps the source digest)."""
+    try:
+        from pyotf_b200 import build as _build
+
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("source_digest") != _build._digest():
+            return None, None, "profiles/k1_traffic.json was captured from other kernel sources than this run's: not reported"
+        rec = tj.get(precision) or {}
+        return rec.get("dram_bytes"), rec.get("warp_instructions"), tj.get("note")
+    except Exception as e:                                  # no capture committed
+        return None, None, f"no ncu capture ({e.__class__.__name__})"
+
+
+def measure_k1(precision, args, rank, world, local, dist, sample_clocks):
+    """cfg1 through pyotf_b200_hanser_psf_zhost (host zrange, the call HanserPSF.PSFi makes), through
+    pyotf_b200_hanser_psf (device zrange) and end to end through the Python API, in one precision."""
     import torch
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from pyotf_b200 import _engine as eng
     from pyotf_b200 import _lib
     from pyotf_b200.otf import HanserPSF
 
-    numa_node = eng.bind_to_gpu_numa_node(local) if world > 1 else None   # before any pinned allocation
-    precision = args.precision
     rt = torch.float32 if precision == "fp32" else torch.float64
     esize = 4 if precision == "fp32" else 8
     N, nz = CFG1["size"], CFG1["zsize"]
     # weak scaling: rank r owns planes [r*nz, (r+1)*nz) of an nz*world-plane stack
     zall = (np.arange(nz * world) - (nz * world + 1) // 2) * CFG1["zres"]
-    zr = zall[rank * nz:(rank + 1) * nz].astype(np.float64)
+    zr = np.ascontiguousarray(zall[rank * nz:(rank + 1) * nz].astype(np.float64))
     h = eng.hanser_handle(CFG1["wl"], CFG1["na"], CFG1["ni"], CFG1["res"], N, "none", "sine", precision, -1)
     zd = eng.to_device_f64(zr)
-    ring = 8  # 8 x 32 MiB (fp32) outputs = 256 MiB > 126 MB L2: every step's stores must reach HBM
+    # 8 x 32 MiB (fp32) / 5 x 64 MiB (fp64) outputs > 126 MB L2: every step's stores must reach HBM
+    ring = 8 if precision == "fp32" else 5
     outs = [torch.empty((1, nz, N, N), dtype=rt, device="cuda") for _ in range(ring)]
     lib = _lib.load()
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
-    # the call HanserPSF.PSFi makes: zrange is a host array (as in the reference) and travels by value in the
-    # kernel arguments, so consecutive stacks overlap (programmatic dependent launch) -- pyotf_b200_hanser_psf_zhost
-    zr = np.ascontiguousarray(zr)
     calls = [(h._h, C.c_void_p(zr.ctypes.data), nz, C.c_void_p(0), 1, 0, C.c_void_p(0), C.c_void_p(o.data_ptr()), sp)
              for o in outs]
     calls_dev = [(h._h, C.c_void_p(zd.data_ptr()), nz, C.c_void_p(0), 1, 0, C.c_void_p(0), C.c_void_p(o.data_ptr()), sp)
@@ -436,16 +444,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+    if sampler:
         sampler.start()
     # keep the GPU busy long enough for nvidia-smi to see clocks under load: repeat the K-step
-    # measurement until >= 0.5 s of device time, report the best repetition (each is exactly K steps)
+    # measurement until >= min_seconds of wall time, report the best repetition (each is exactly K steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps, best_ms, t_wall = 0, None, time.perf_counter()
+    min_s = args.min_seconds if sample_clocks else min(args.min_seconds, 0.3)
     while True:
         barrier()
         e0.record(stream)
@@ -453,18 +469,13 @@ def run_ours(args):
             step(i)
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = allmax(e0.elapsed_time(e1))
         best_ms = ms if best_ms is None else min(best_ms, ms)
         reps += 1
-        if time.perf_counter() - t_wall > args.min_seconds or reps >= 200:
+        if time.perf_counter() - t_wall > min_s or reps >= 200:
             break
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
     ms_per_step = best_ms / args.steps
-    planes_per_s = nz * world / (ms_per_step * 1e-3)
     # z on the device (pyotf_b200_hanser_psf, no promise about who wrote it): every launch waits for its
     # predecessor before it reads anything, so consecutive stacks do not overlap
     for i in range(3):
@@ -479,11 +490,7 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         serial_ms = ms if serial_ms is None else min(serial_ms, ms)
-    if dist is not None:
-        t = torch.tensor([serial_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        serial_ms = float(t.item())
-    serial_ms /= args.steps
+    serial_ms = allmax(serial_ms) / args.steps
 
     # ---- e2e through the public API: host zrange in, host PSFi (numpy) out, every step ----
     model = HanserPSF(precision=precision, **CFG1)
@@ -499,80 +506,108 @@ def run_ours(args):
         model.zrange = z_host.numpy()
         p = model.PSFi
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / ksteps
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    assert p.shape == (nz, N, N)
+    e2e_s = allmax((time.perf_counter() - t0) / ksteps)
+    assert p.shape == (nz, N, N) and p.dtype == (np.float32 if precision == "fp32" else np.float64)
+    del outs
+    torch.cuda.empty_cache()
+    peak, peak_src = measured_peaks()
+    alg_bytes = nz * N * N * esize  # N^2 * s_r per plane -> PSFi only
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic, winst, traffic_note = k1_traffic(precision)
+    binding = None
+    if winst:
+        props = torch.cuda.get_device_properties(torch.cuda.current_device())
+        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        min_us = winst / (props.multi_processor_count * 4) / mhz
+        binding = {"kind": "instruction issue", "warp_instructions_per_launch": winst,
+                   "schedulers": props.multi_processor_count * 4, "sm_mhz": mhz, "min_us_at_one_issue_per_cycle": min_us,
+                   "frac": min_us / (ms_per_step * 1e3), "source": "smsp__inst_executed.sum of the stamped ncu capture"}
+    return {
+        "precision": precision, "reps": reps, "ring": ring, "clocks": clocks,
+        "ms_per_step": ms_per_step, "planes_per_s": nz * world / (ms_per_step * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                     "kernel": "hanser_sym_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                     "binding_limit": binding,
+                     "device_z_serialized": {
+                         "ms_per_step": serial_ms, "planes_per_s": nz * world / (serial_ms * 1e-3),
+                         "achieved": alg_bytes / (serial_ms * 1e-3) / 1e9,
+                         "frac": alg_bytes / (serial_ms * 1e-3) / 1e9 / peak,
+                         "note": "pyotf_b200_hanser_psf with zrange in device memory: each launch waits for its "
+                                 "predecessor before reading anything (consecutive stacks do not overlap)"}},
+        "e2e": {"value": nz * world / e2e_s, "unit": "planes/s", "h2d_bytes_per_step": int(zr.nbytes),
+                "d2h_bytes_per_step": int(nz * N * N * esize), "ms_per_step": 1e3 * e2e_s,
+                "path": "HanserPSF.zrange = host array; HanserPSF.PSFi -> numpy (pinned D2H)"},
+    }
 
-    pr = None
+
+def run_ours(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from pyotf_b200 import _engine as eng
+
+    numa_node = eng.bind_to_gpu_numa_node(local) if world > 1 else None   # before any pinned allocation
+    precision = args.precision
+    other = "fp64" if precision == "fp32" else "fp32"
+    k1 = measure_k1(precision, args, rank, world, local, dist, True)
+    # the same measurement in the other precision (fp64 = the reference's own arithmetic, pyotf/otf.py:426)
+    k1_other = measure_k1(other, args, rank, world, local, dist, False) if not args.single_precision else None
+
+    pr = pr_other = None
     if not args.no_pr:
         pr = bench_pr(precision, rank, world, dist)
+        if not args.single_precision:
+            pr_other = bench_pr(other, rank, world, dist, reps=3, extras=False)
     others = None
     if not args.no_others:
         others = bench_other_configs(precision, rank, world)
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        alg_bytes = nz * N * N * esize  # N^2 * s_r per plane -> PSFi only
-        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-        traffic, traffic_note = None, None
-        try:
-            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-                tj = json.load(f)
-            traffic, traffic_note = tj.get(precision), tj.get("_note")
-            winst = tj.get("warp_instructions_" + precision)
-        except Exception:
-            winst = None
-        # the limit that actually binds K1: warp instructions over the SM sub-partition
-        # schedulers at one issue per cycle, next to the HBM figure the contract asks for
-        binding = None
-        if winst:
-            props = torch.cuda.get_device_properties(torch.cuda.current_device())
-            mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
-            min_us = winst / (props.multi_processor_count * 4) / mhz
-            binding = {"kind": "instruction issue", "warp_instructions_per_launch": winst,
-                       "schedulers": props.multi_processor_count * 4, "sm_mhz": mhz, "min_us_at_one_issue_per_cycle": min_us,
-                       "frac": min_us / (ms_per_step * 1e3),
-                       "source": "smsp__inst_executed.sum, ncu --set full (profiles/r1_hot_kernels_ncu.md)"}
+        nz = CFG1["zsize"]
         line = {
-            "metric": "HanserPSF z-planes/s at 256^2", "value": planes_per_s, "unit": "planes/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "metric": "HanserPSF z-planes/s at 256^2", "value": k1["planes_per_s"], "unit": "planes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": k1["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if precision == "fp32" else "f64", "data": "synthetic",
-            "config": {"workload": "hanser256: HanserPSF(wl=520,na=0.85,ni=1.0,res=130,zres=300,size=256,"
-                                   "zsize=128) -> PSFi (BASELINE config 1)",
-                       "step": "one fused K1 launch over the 128-plane stack per GPU through pyotf_b200_hanser_psf_zhost "
-                               "(the call HanserPSF.PSFi makes: zrange by value in the kernel arguments; consecutive "
-                               "stacks overlap by programmatic dependent launch, each waits for its predecessor "
-                               "before its first store)",
-                       "l2": "outputs rotate over 8 x 32 MiB buffers (256 MiB > 126 MB L2)",
-                       "timing": f"best of {reps} repetitions of exactly {args.steps} steps, CUDA events on the "
+            "config": {"workload": WORKLOAD,
+                       "step": "one fused K1 launch over the 128-plane stack per GPU (one CTA per plane) through "
+                               "pyotf_b200_hanser_psf_zhost, the call HanserPSF.PSFi makes: zrange by value in the kernel "
+                               "arguments; consecutive stacks overlap by programmatic dependent launch (a launch whose "
+                               "output is disjoint from the launches still in flight only has to finish after them, "
+                               "one that overwrites a recent output waits before its first store)",
+                       "l2": f"outputs rotate over {k1['ring']} buffers of {nz * 65536 * (4 if precision == 'fp32' else 8) >> 20} MiB "
+                             f"(> 126 MB L2)",
+                       "timing": f"best of {k1['reps']} repetitions of exactly {args.steps} steps, CUDA events on the "
                                  f"launch stream, max over ranks",
                        "parallelism": f"z-shard x{world} (no collective)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
-                         "kernel": "hanser_psf_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                         "binding_limit": binding,
-                         "device_z_serialized": {
-                             "ms_per_step": serial_ms, "planes_per_s": nz * world / (serial_ms * 1e-3),
-                             "achieved": alg_bytes / (serial_ms * 1e-3) / 1e9,
-                             "frac": alg_bytes / (serial_ms * 1e-3) / 1e9 / peak,
-                             "note": "pyotf_b200_hanser_psf with zrange in device memory: each launch waits for its "
-                                     "predecessor before reading anything (consecutive stacks do not overlap)"}},
-            "clocks": clocks,
-            "e2e": {"value": nz * world / e2e_s, "unit": "planes/s", "h2d_bytes_per_step": int(zr.nbytes),
-                    "d2h_bytes_per_step": int(nz * N * N * esize), "ms_per_step": 1e3 * e2e_s,
-                    "path": "HanserPSF.zrange = host array; HanserPSF.PSFi -> numpy (pinned D2H)",
-                    "numa_node_rank0": numa_node},
-            # per step: one hanser_psf_kernel launch (256 CTAs of 128 rows; every CTA builds its plane's defocus table)
+            "roofline": k1["roofline"],
+            "clocks": k1["clocks"],
+            "e2e": dict(k1["e2e"], numa_node_rank0=numa_node),
+            # per step: one hanser_sym_kernel launch (128 CTAs, one per plane; every CTA builds its plane's defocus table)
             "gpu_launches": args.steps,
         }
+        if k1_other is not None:
+            # the other precision mode, same workload / timing protocol (fp64: the reference arm's arithmetic)
+            line[other] = {"value": k1_other["planes_per_s"], "unit": "planes/s", "ms_per_step": k1_other["ms_per_step"],
+                           "dtype": "f64" if other == "fp64" else "f32", "roofline": k1_other["roofline"],
+                           "e2e": k1_other["e2e"],
+                           "l2": f"outputs rotate over {k1_other['ring']} buffers (> 126 MB L2)"}
         if others is not None:
             line["other_configs"] = others       # rank 0's shard only
         if pr is not None:
             line["phase_retrieval"] = pr
+            if pr_other is not None:
+                pr[other] = pr_other
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_hanser()
             if pr is not None:
@@ -594,6 +629,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-pr", action="store_true", help="skip the phase-retrieval leg")
     ap.add_argument("--no-others", action="store_true", help="skip the config 3/4/5 legs")
+    ap.add_argument("--single-precision", action="store_true", help="skip the sub-records in the other precision mode")
     ap.add_argument("--min-seconds", type=float, default=1.0,
                     help="repeat the K-step measurement for at least this long (clock sampling); 0 = once")
     args = ap.parse_args()

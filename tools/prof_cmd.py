@@ -25,9 +25,11 @@ def main():
     torch.cuda.set_device(0)
     if "k1" in what:
         h = eng.hanser_handle(520, 0.85, 1.0, 130, 256, "none", "sine", precision, -1)
-        z = eng.to_device_f64((np.arange(128) - 64) * 300.0)
-        for _ in range(4):
-            _, psfi = h.psf(z)
+        z = (np.arange(128) - 64) * 300.0          # host zrange: the call HanserPSF.PSFi makes
+        outs = [None] * 4
+        for i in range(4):
+            _, outs[i] = h.psf(z)
+        psfi = outs[-1]
         torch.cuda.synchronize()
         print("k1 ok", float(psfi.sum()))
     if "pr" in what:
