@@ -124,6 +124,13 @@ class HanserHandle:
             stride = self.KR * self.K if pupilc.shape[0] > 1 else 0
             if pupilc.shape[0] > 1:
                 batch = pupilc.shape[0]
+        for name, out, dt, shape in (("psfa_out", psfa_out, ct, (batch, self.nvec, nz, N, N)),
+                                     ("psfi_out", psfi_out, rt, (batch, nz, N, N))):
+            # the C side writes through the raw pointer: anything but a matching contiguous CUDA tensor would be an
+            # out-of-bounds or garbled device write
+            if out is not None and not (torch.is_tensor(out) and out.is_cuda and out.is_contiguous() and out.dtype == dt
+                                        and tuple(out.shape) == shape):
+                raise ValueError(f"{name} must be a contiguous CUDA tensor of dtype {dt} and shape {shape}")
         if want_psfa and psfa_out is None:
             psfa_out = torch.empty((batch, self.nvec, nz, N, N), dtype=ct, device="cuda")
         if want_psfi and psfi_out is None:
@@ -299,9 +306,12 @@ _handles_lock = threading.Lock()
 
 
 def hanser_handle(wl, na, ni, res, size, vec_corr, condition, precision, support):
+    """Cached pyotf_hanser handle.  A handle owns per-launch scratch (pre-multiplied pupils, per-plane defocus
+    tables, uploaded plane positions) that the C side overwrites and regrows on every launch, so it must never be
+    shared between host threads or CUDA streams: both are part of the cache key."""
     torch = _torch()
     key = (float(wl), float(na), float(ni), float(res), int(size), vec_corr, condition, precision, int(support),
-           torch.cuda.current_device())
+           torch.cuda.current_device(), int(torch.cuda.current_stream().cuda_stream), threading.get_ident())
     with _handles_lock:
         h = _handles.get(key)
         if h is None:
@@ -412,24 +422,43 @@ def aberration_pupil(handle, n, m, mcoefs, pcoefs):
     return out
 
 
-_pinned_pool = []          # [pinned tensor, weakref to the numpy view handed out]
+_pinned_pool = []          # [pinned tensor, weakref to the numpy view handed out | _CLAIMED]
 _PINNED_POOL_MAX = 8
+_PINNED_POOL_BYTES = 256 << 20      # at most this much pinned host memory is retained for reuse
+_CLAIMED = object()                 # slot handed to a thread whose copy is still in flight
+
+
+def _slot_free(ref):
+    return ref is None or (ref is not _CLAIMED and ref() is None)
 
 
 def _pinned_like(t):
     """(slot) with a pinned host tensor of t's shape/dtype.  cudaHostAlloc costs milliseconds for a 32 MiB
-    stack, so a buffer is recycled once the numpy array handed out for it (and every view of it) is gone."""
+    stack, so a buffer is recycled once the numpy array handed out for it (and every view of it) is gone.
+    The slot is claimed while the lock is held (two threads never get the same buffer); buffers beyond the
+    byte cap are one-off allocations that are not retained."""
     torch = _torch()
+    nbytes = t.numel() * t.element_size()
     with _handles_lock:
         for i, slot in enumerate(_pinned_pool):
             buf, ref = slot
-            if buf.dtype == t.dtype and buf.shape == t.shape and (ref is None or ref() is None):
+            if buf.dtype == t.dtype and buf.shape == t.shape and _slot_free(ref):
+                slot[1] = _CLAIMED
                 _pinned_pool.append(_pinned_pool.pop(i))
                 return slot
-        slot = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True), None]
+        slot = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True), _CLAIMED]
+        if nbytes > _PINNED_POOL_BYTES:
+            return slot                                   # too large to keep around
         _pinned_pool.append(slot)
-        while len(_pinned_pool) > _PINNED_POOL_MAX:
-            _pinned_pool.pop(0)
+        total = sum(b.numel() * b.element_size() for b, _ in _pinned_pool)
+        i = 0
+        while (len(_pinned_pool) > _PINNED_POOL_MAX or total > _PINNED_POOL_BYTES) and i < len(_pinned_pool) - 1:
+            b, ref = _pinned_pool[i]
+            if _slot_free(ref):                           # drop idle buffers only, oldest first
+                total -= b.numel() * b.element_size()
+                _pinned_pool.pop(i)
+            else:
+                i += 1
         return slot
 
 
