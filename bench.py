@@ -228,8 +228,9 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100, extras=True):
            "scaling": "strong", "dtype": "f32" if precision == "fp32" else "f64",
            "workload": "retrieve_phase on the 25 x 256^2 fixture stack, 100 iterations, tol 0 (BASELINE config 2)",
            "rows_per_cta": st.rows_per_cta, "ctas_per_iteration": st.nparts,
-           "kernels_per_iteration": 2 if world == 1 else 4, "final_mse": float(mse[-1]),
-           "parallelism": f"z-shard x{world}" + ("" if world == 1 else " + 1 NCCL all-reduce / iteration")}
+           "kernels_per_iteration": 2 if world == 1 else 3, "final_mse": float(mse[-1]),
+           "parallelism": f"z-shard x{world}" + ("" if world == 1 else " + per-iteration sum over ranks inside the finalize "
+                                                                      "kernel (peer windows over NVLink, no NCCL call)")}
     # roofline of one iteration: nz*N^2*s_r of measured data + 2 compact... full-grid pupils (in/out)
     es = 4 if precision == "fp32" else 8
     alg = nz_total * 256 * 256 * es + 2 * 256 * 256 * 2 * es
@@ -309,13 +310,39 @@ def _time_gpu(fn, reps, warmup=2):
     return best
 
 
-def bench_other_configs(precision, rank, world):
-    """Device-resident throughput of BASELINE configs 3, 4 and 5 on this rank's shard (short runs; the
-    parity of each config is covered by tests/, these are the numbers DESIGN.md quotes)."""
+def _time_gpu_ranks(fn, reps, dist, warmup=1):
+    """Best over `reps` of the max-over-ranks CUDA-event time (ms) of fn(), every repetition behind a barrier."""
+    import torch
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(warmup):
+        fn()
+    best = None
+    for _ in range(reps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        best = ms if best is None else min(best, ms)
+    return best
+
+
+def bench_other_configs(precision, rank, world, dist=None):
+    """Device-resident throughput of BASELINE configs 3, 4 and 5.  Configs 4 and 5 are multi-GPU workloads: every rank
+    runs its WHOLE shard (1024 / world planes of the 1024^2 stack; 8192 / world library entries), the time is the max over
+    ranks and the rates are whole-job aggregates.  (Parity of each config is covered by tests/.)"""
     import torch
 
     from pyotf_b200 import _engine as eng
-    from pyotf_b200 import _fft, _sheppard
+    from pyotf_b200 import _fft
     from pyotf_b200.otf import HanserPSF, SheppardPSF, _aberrated_pupils
 
     out = {}
@@ -326,60 +353,117 @@ def bench_other_configs(precision, rank, world):
     coefs = np.random.default_rng(0).standard_normal((8192, 120)) * 0.1
     lo, hi = eng.shard_bounds(8192, rank, world)
     B = 128                                                   # entries per launch: 2.1 GiB of fp32 PSFi
-    mine = coefs[lo:hi][:4 * B]
+    mine = coefs[lo:hi]
     ring = [torch.empty((B, 64, 256, 256), dtype=rt, device="cuda") for _ in range(2)]
     z = eng.to_device_f64(base.zrange)
-    pc = [eng.to_device_f64(mine[i * B:(i + 1) * B]) for i in range(len(mine) // B)]
-    state = {"i": 0}
+    pc = [eng.to_device_f64(mine[i:i + B]) for i in range(0, len(mine), B)]
 
-    def lib_step():
-        i = state["i"] = state["i"] + 1
-        pupils = _aberrated_pupils(base, None, pc[i % len(pc)])
-        pupils.handle(base).psf(z, pupils.tensor, want_psfa=False, want_psfi=True, psfi_out=ring[i % 2])
+    def lib_shard():
+        for i, c in enumerate(pc):
+            pupils = _aberrated_pupils(base, None, c)
+            o = ring[i % 2] if c.shape[0] == B else ring[i % 2][:c.shape[0]]
+            pupils.handle(base).psf(z, pupils.tensor, want_psfa=False, want_psfi=True, psfi_out=o)
 
-    ms = _time_gpu(lib_step, reps=4)
-    out["library_cfg5"] = {"entries_per_s": B / (ms * 1e-3), "planes_per_s": B * 64 / (ms * 1e-3), "ms_per_launch": ms,
-                           "entries_per_launch": B, "achieved_GBps": B * 64 * 256 * 256 * es / (ms * 1e-3) / 1e9,
-                           "note": "120 Noll coefs -> aberrated pupil kernel + K1 per launch; outputs alternate over "
-                                   "2 x 2.1 GiB buffers (the 8192-entry library is 137 GB: streamed, never resident)"}
-    del ring
-    # ---- config 4: 1024^2 planes with 15 Zernike phase terms, z-sharded --------------------------------------
+    ms = _time_gpu_ranks(lib_shard, 2, dist)
+    out["library_cfg5"] = {"entries_per_s": 8192 / (ms * 1e-3), "planes_per_s": 8192 * 64 / (ms * 1e-3), "ms_whole_library": ms,
+                           "entries": 8192, "entries_per_rank": len(mine), "entries_per_launch": B, "n_gpus": world,
+                           "achieved_GBps_per_gpu": len(mine) * 64 * 256 * 256 * es / (ms * 1e-3) / 1e9,
+                           "scaling": "strong (the whole 8192-entry library, batch-sharded; max over ranks)",
+                           "note": "120 Noll coefs -> aberrated pupil kernel + K1 per 128-entry launch; outputs alternate over "
+                                   "2 x 2.1 GiB buffers (the library is 137 GB of PSFi: streamed, never resident)"}
+    del ring, pc
+    torch.cuda.empty_cache()
+    # ---- config 4: 1024^2 x 1024 planes with 15 Zernike phase terms, z-sharded --------------------------------
     big = HanserPSF(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=1024, zsize=1024, precision=precision)
     lo, hi = eng.shard_bounds(1024, rank, world)
-    zc = eng.to_device_f64(big.zrange[lo:hi][:64])
+    chunk = 64
+    zcs = [eng.to_device_f64(big.zrange[a:min(a + chunk, hi)]) for a in range(lo, hi, chunk)]
     pup = _aberrated_pupils(big, None, (np.random.default_rng(0).standard_normal(15) * 0.2)[None])
     hb = pup.handle(big)
-    outb = [torch.empty((1, 64, 1024, 1024), dtype=rt, device="cuda") for _ in range(2)]
-    state["i"] = 0
+    outb = [torch.empty((1, chunk, 1024, 1024), dtype=rt, device="cuda") for _ in range(2)]
 
-    def big_step():
-        i = state["i"] = state["i"] + 1
-        hb.psf(zc, pup.tensor, want_psfa=False, want_psfi=True, psfi_out=outb[i % 2])
+    def big_shard():
+        for i, zc in enumerate(zcs):
+            o = outb[i % 2] if zc.numel() == chunk else outb[i % 2][:, :zc.numel()].contiguous()
+            hb.psf(zc, pup.tensor, want_psfa=False, want_psfi=True, psfi_out=o)
 
-    ms = _time_gpu(big_step, reps=4)
-    out["hanser1024_cfg4"] = {"planes_per_s": 64 / (ms * 1e-3), "ms_per_64_planes": ms,
-                              "achieved_GBps": 64 * 1024 * 1024 * es / (ms * 1e-3) / 1e9,
-                              "note": "two-pass K1b, 64-plane chunk of the 1024-plane stack per step"}
+    ms = _time_gpu_ranks(big_shard, 2, dist)
+    out["hanser1024_cfg4"] = {"planes_per_s": 1024 / (ms * 1e-3), "ms_whole_stack": ms, "planes": 1024, "planes_per_rank": hi - lo,
+                              "n_gpus": world, "achieved_GBps_per_gpu": (hi - lo) * 1024 * 1024 * es / (ms * 1e-3) / 1e9,
+                              "scaling": "strong (the whole 1024-plane stack, z-sharded; max over ranks)",
+                              "note": "two-pass K1b in 64-plane chunks (outputs alternate over 2 x 256 MiB buffers)"}
     del outb
-    # ---- config 3: SheppardPSF 256^3 (zres=190; the 200 of BASELINE.json raises ValueError in the reference) ----
-    sh = SheppardPSF(wl=520, na=1.27, ni=1.33, res=100, zres=190, size=256, zsize=256, precision=precision)
+    torch.cuda.empty_cache()
+    if rank == 0:
+        # ---- config 3: SheppardPSF 256^3 (zres=190; the 200 of BASELINE.json raises ValueError in the reference) ----
+        sh = SheppardPSF(wl=520, na=1.27, ni=1.33, res=100, zres=190, size=256, zsize=256, precision=precision)
 
-    def shep_step():
-        sh._attribute_changed()
-        return sh.PSFi_dev
+        def shep_step():
+            sh._attribute_changed()
+            return sh.PSFi_dev
 
-    ms = _time_gpu(shep_step, reps=4)
-    out["sheppard_cfg3"] = {"volumes_per_s": 1 / (ms * 1e-3), "ms_per_volume": ms,
-                            "achieved_GBps": 256 ** 3 * es / (ms * 1e-3) / 1e9,
-                            "note": "shell generator + shifted 3D inverse FFT + |.|^2 -> PSFi (replicas only across GPUs)"}
-    # ---- config 1 epilogue: OTFi from the resident PSFi --------------------------------------------------------
-    m = HanserPSF(precision=precision, **CFG1)
-    psfi = m.PSFi_dev
-    ms = _time_gpu(lambda: _fft.shifted_fft_dev(psfi, axes=None, inverse=False), reps=4)
-    out["otfi_cfg1"] = {"ms": ms, "achieved_GBps": 128 * 256 * 256 * 3 * es / (ms * 1e-3) / 1e9,
-                        "note": "shifted 3D FFT of the resident 128 x 256^2 PSFi (algorithmic bytes: real read + complex write)"}
+        ms = _time_gpu(shep_step, reps=4)
+        out["sheppard_cfg3"] = {"volumes_per_s": 1 / (ms * 1e-3), "ms_per_volume": ms,
+                                "achieved_GBps": 256 ** 3 * es / (ms * 1e-3) / 1e9,
+                                "note": "shell generator + shifted 3D inverse FFT + |.|^2 -> PSFi (replicas only across GPUs)"}
+        # ---- config 1 epilogue: OTFi from the resident PSFi --------------------------------------------------------
+        m = HanserPSF(precision=precision, **CFG1)
+        psfi = m.PSFi_dev
+        ms = _time_gpu(lambda: _fft.shifted_fft_dev(psfi, axes=None, inverse=False), reps=4)
+        out["otfi_cfg1"] = {"ms": ms, "achieved_GBps": 128 * 256 * 256 * 3 * es / (ms * 1e-3) / 1e9,
+                            "note": "shifted 3D FFT of the resident 128 x 256^2 PSFi (algorithmic bytes: real read + complex write)"}
+    if dist is not None:
+        # OTFi of a z-sharded stack (cfg1 planes per rank, all-gather or all-to-all, pyotf_b200/_dist.py)
+        from pyotf_b200 import _dist
+
+        nzl = CFG1["zsize"]
+        zall = (np.arange(nzl * world) - (nzl * world + 1) // 2) * CFG1["zres"]
+        mloc = HanserPSF(wl=CFG1["wl"], na=CFG1["na"], ni=CFG1["ni"], res=CFG1["res"], size=CFG1["size"],
+                         zrange=zall[rank * nzl:(rank + 1) * nzl], precision=precision)
+        pl = mloc.PSFi_dev
+        for mode in ("gather", "alltoall"):
+            ms = _time_gpu_ranks(lambda: _dist.otfi_zsharded(pl, nzl * world, mode=mode), 3, dist)
+            out[f"otfi_zsharded_{mode}"] = {"ms": ms, "planes": nzl * world, "planes_per_rank": nzl, "n_gpus": world,
+                                            "note": "PSFi resident and z-sharded -> this rank's z block of OTFi of the whole stack"}
     torch.cuda.empty_cache()
     return out
+
+
+def bench_pr_weak(precision, rank, world, dist, planes_per_rank=128, iters=20, reps=3):
+    """Phase retrieval, weak scaling: a synthetic stack of planes_per_rank * world planes (the PSFi of a pupil with
+    random Noll 5-15 magnitude / phase terms, the recipe of the reference's tests/integration_test.py:50-58), z-sharded.
+    Every iteration sums the per-rank partial pupils across the ranks inside the finalize kernel (peer windows)."""
+    import torch
+
+    from pyotf_b200 import _engine as eng
+    from pyotf_b200.otf import HanserPSF, apply_aberration
+
+    nzt = planes_per_rank * world
+    zall = (np.arange(nzt) - (nzt + 1) // 2) * PR_PARAMS["zres"]
+    zloc = zall[rank * planes_per_rank:(rank + 1) * planes_per_rank].astype(np.float64)
+    rng = np.random.default_rng(12345)
+    pc, mc = np.zeros(15), np.zeros(15)
+    pc[4:], mc[4:] = rng.random(11), rng.random(11)
+    model = HanserPSF(wl=PR_PARAMS["wl"], na=PR_PARAMS["na"], ni=PR_PARAMS["ni"], res=PR_PARAMS["res"], size=256,
+                      zrange=zloc, vec_corr="none", condition="none", precision=precision)
+    data = (apply_aberration(model, mc, pc).PSFi_dev * 1e4).contiguous()
+    st = eng.PRState(PR_PARAMS["wl"], PR_PARAMS["na"], PR_PARAMS["ni"], PR_PARAMS["res"], 256, zloc, data, precision,
+                     nz_total=nzt)
+    comm = eng.Comm(rank, world) if world > 1 else None
+    state = {}
+
+    def run():
+        st.set_pupil(None)
+        state["mse"] = st.run(iters, 0.0, 0.0, comm=comm)[0]
+
+    ms = _time_gpu_ranks(run, reps, dist)
+    if comm is not None:
+        comm.close()
+    return {"us_per_iter": 1e3 * ms / iters, "iters_per_s": iters / (ms * 1e-3), "plane_iters_per_s": nzt * iters / (ms * 1e-3),
+            "planes_per_rank": planes_per_rank, "planes_total": nzt, "n_gpus": world, "iters": iters, "scaling": "weak",
+            "dtype": "f32" if precision == "fp32" else "f64", "final_mse": float(state["mse"][-1]),
+            "note": "synthetic stack (Noll 5-15 pupil), z-sharded; set_pupil + the 20-iteration loop inside the timed region; "
+                    "weak-scaling efficiency = us_per_iter at 1 GPU / us_per_iter at N"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -568,9 +652,12 @@ def run_ours(args):
         pr = bench_pr(precision, rank, world, dist)
         if not args.single_precision:
             pr_other = bench_pr(other, rank, world, dist, reps=3, extras=False)
+    pr_weak = None
+    if not args.no_pr:
+        pr_weak = bench_pr_weak(precision, rank, world, dist)
     others = None
     if not args.no_others:
-        others = bench_other_configs(precision, rank, world)
+        others = bench_other_configs(precision, rank, world, dist)
 
     if rank == 0:
         nz = CFG1["zsize"]
@@ -602,8 +689,10 @@ def run_ours(args):
                            "dtype": "f64" if other == "fp64" else "f32", "roofline": k1_other["roofline"],
                            "e2e": k1_other["e2e"],
                            "l2": f"outputs rotate over {k1_other['ring']} buffers (> 126 MB L2)"}
+        if pr_weak is not None:
+            line["phase_retrieval_weak"] = pr_weak
         if others is not None:
-            line["other_configs"] = others       # rank 0's shard only
+            line["other_configs"] = others       # whole-job aggregates over all ranks (max-over-ranks time)
         if pr is not None:
             line["phase_retrieval"] = pr
             if pr_other is not None:

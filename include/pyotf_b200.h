@@ -204,6 +204,20 @@ int pyotf_b200_pr_run(pyotf_pr_t* s, int max_iters, double pupil_tol, double mse
                       pyotf_comm_t* comm, double* mse_host, double* mse_diff_host, double* pupil_diff_host,
                       int* iters_run_host, void* stream);
 
+/* z-sharded phase retrieval without a collective library call per iteration: every rank exports a small window
+ * through CUDA IPC and maps the windows of all other ranks of the box.  Each iteration, CTA b of a rank's finalize
+ * kernel sums the rank's partial pupils for its 32 pixels, stores them into entry [rank] of EVERY window (posted
+ * writes over NVLink, every 16-byte word carrying the iteration's epoch next to its payload), spins on the words of
+ * CTA b of all ranks in its own window until they carry the epoch, and adds them in rank order: no fence, no
+ * round trip; all ranks compute bit-identical pupils and stop at the same iteration, with two
+ * kernels per iteration exactly like the single-GPU loop.  This replaces the ncclAllReduce that the reference's
+ * single-process loop has no counterpart for:
+ *   1. pr_window_alloc on every rank -> 64-byte handle;  2. exchange the handles (any transport);
+ *   3. pr_window_open(all handles in rank order).  pr_run(comm != NULL) then uses the window.
+ * One process per GPU, all GPUs on one node with peer access (NVLink / NVSwitch). */
+int pyotf_b200_pr_window_alloc(pyotf_pr_t* s, int world, unsigned char handle_out[64]);
+int pyotf_b200_pr_window_open(pyotf_pr_t* s, const unsigned char* handles /* [world][64] */, int rank, int world);
+
 /* HOST function (host pointers): 2D phase unwrapping of one ny x nx image of wrapped phases,
  * Herraez et al. 2002 -- stand-in for skimage.restoration.unwrap_phase (phaseretrieval.py:146). */
 int pyotf_b200_unwrap_phase_2d(const double* in_host, double* out_host, int ny, int nx);

@@ -191,8 +191,35 @@ class PRState:
         _lib.check(_lib.load().pyotf_b200_pr_get_pupil(self._h, int(bool(applied)), ptr(out), stream_ptr()))
         return out
 
+    def open_window(self, comm):
+        """z-sharded runs: export this state's partial-sum window and map every other rank's (CUDA IPC; the
+        handles travel through torch.distributed).  Collective over the ranks of `comm`; idempotent."""
+        if getattr(self, "_window", False) or comm is None or comm.world < 2:
+            return
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        mine = (C.c_ubyte * 64)()
+        if os.environ.get("PYOTF_B200_PR_SELFWIN"):     # timing experiment: the window kernel without any peer (wrong sums)
+            _lib.check(lib.pyotf_b200_pr_window_alloc(self._h, 1, C.cast(mine, C.c_void_p)))
+            _lib.check(lib.pyotf_b200_pr_window_open(self._h, C.cast(mine, C.c_void_p), 0, 1))
+            self._window = True
+            return
+        _lib.check(lib.pyotf_b200_pr_window_alloc(self._h, int(comm.world), C.cast(mine, C.c_void_p)))
+        allh = [None] * comm.world
+        dist.all_gather_object(allh, bytes(mine))
+        buf = (C.c_ubyte * (64 * comm.world)).from_buffer_copy(b"".join(allh))
+        _lib.check(lib.pyotf_b200_pr_window_open(self._h, C.cast(buf, C.c_void_p), int(comm.rank), int(comm.world)))
+        dist.barrier()
+        self._window = True
+
     def run(self, max_iters, pupil_tol, mse_tol, phase_only=False, comm=None):
-        """Iterate on the device; returns (mse, mse_diff, pupil_diff) trimmed to the iterations run."""
+        """Iterate on the device; returns (mse, mse_diff, pupil_diff) trimmed to the iterations run.
+        With `comm` (one rank per GPU) the stack is z-sharded: the per-iteration sum over ranks runs inside the
+        finalize kernel through peer-mapped windows (`open_window`, done on first use unless
+        PYOTF_B200_PR_NCCL is set, which keeps the NCCL all-reduce)."""
+        if comm is not None and not os.environ.get("PYOTF_B200_PR_NCCL"):
+            self.open_window(comm)
         mse, msed, pd = (np.empty(int(max_iters), dtype=np.float64) for _ in range(3))
         n = C.c_int(0)
         _lib.check(_lib.load().pyotf_b200_pr_run(

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "pyotf_b200_pr_set_pupil": (_i, [_vp, _vp, _vp]),
     "pyotf_b200_pr_get_pupil": (_i, [_vp, _i, _vp, _vp]),
     "pyotf_b200_pr_run": (_i, [_vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _ip, _vp]),
+    "pyotf_b200_pr_window_alloc": (_i, [_vp, _i, _vp]),
+    "pyotf_b200_pr_window_open": (_i, [_vp, _vp, _i, _i]),
     "pyotf_b200_unwrap_phase_2d": (_i, [_vp, _vp, _i, _i]),
     "pyotf_b200_comm_load": (_i, [C.c_char_p]),
     "pyotf_b200_comm_unique_id": (_i, [_vp]),

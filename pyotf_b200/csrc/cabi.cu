@@ -1,9 +1,12 @@
 // extern "C" boundary: argument validation, handle lifetime, dtype dispatch.
+#include <cstring>
+
 #include "common.cuh"
 #include "hanser.cuh"
 #include "zernike.cuh"
 #include "sheppard.cuh"
 #include "prep.cuh"
+#include "pr.cuh"
 
 namespace pyotf {
 static thread_local std::string g_last_error;
@@ -385,9 +388,50 @@ int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev,
     return 0;
 }
 
+int pyotf_b200_pr_window_alloc(pyotf_pr_t* s, int world, unsigned char handle_out[64]) {
+    PYOTF_REQUIRE(s && handle_out, "pr_window_alloc: null argument");
+    PYOTF_REQUIRE(world >= 1 && world <= PYOTF_MAX_PEERS, "pr_window_alloc: bad world size");
+    PYOTF_REQUIRE(!s->win, "pr_window_alloc: the state already has a window");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    const int KK = s->h->K * s->h->K;
+    s->win_bytes = pr_win_bytes(KK, s->nblk, world);
+    s->win_alloc_world = world;
+    PYOTF_CUDA_OK(cudaMalloc(&s->win, s->win_bytes));            // exportable: not from the stream-ordered pool
+    PYOTF_CUDA_OK(cudaMemset(s->win, 0, s->win_bytes));
+    PYOTF_CUDA_OK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t hnd;
+    PYOTF_CUDA_OK(cudaIpcGetMemHandle(&hnd, s->win));
+    std::memcpy(handle_out, &hnd, 64);
+    return 0;
+}
+
+int pyotf_b200_pr_window_open(pyotf_pr_t* s, const unsigned char* handles, int rank, int world) {
+    PYOTF_REQUIRE(s && handles && s->win, "pr_window_open: call pr_window_alloc first");
+    PYOTF_REQUIRE(world == s->win_alloc_world && rank >= 0 && rank < world, "pr_window_open: bad rank / world");
+    PYOTF_REQUIRE(s->win_world == 0, "pr_window_open: the window is already open");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { s->peer[r] = s->win; continue; }
+        cudaIpcMemHandle_t hnd;
+        std::memcpy(&hnd, handles + (size_t)r * 64, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&s->peer[r], hnd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q) if (q != rank && s->peer[q]) { cudaIpcCloseMemHandle(s->peer[q]); s->peer[q] = nullptr; }
+            set_error(std::string("pr_window_open: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            return 2;
+        }
+    }
+    s->win_rank = rank; s->win_world = world; s->epoch_base = 0;
+    return 0;
+}
+
 int pyotf_b200_pr_destroy(pyotf_pr_t* s) {
     if (!s) return 0;
     cudaStream_t st = s->stream;
+    if (s->win) {
+        cudaStreamSynchronize(st);
+        for (int r = 0; r < s->win_world; ++r) if (r != s->win_rank && s->peer[r]) cudaIpcCloseMemHandle(s->peer[r]);
+        cudaFree(s->win);
+    }
     void* bufs[] = {s->z, s->data, s->pupil[0], s->pupil[1], s->partial, s->mse_part, s->sums, s->diffpart, s->mse,
                     s->mse_diff, s->pupil_diff, s->state, s->dtab, s->W, s->P};
     for (void* b : bufs) if (b) cudaFreeAsync(b, st);         // stream-ordered: returns to the cached pool

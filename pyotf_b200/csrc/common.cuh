@@ -42,6 +42,7 @@ inline void keep_scratch_pool() {
 }
 
 constexpr int PYOTF_MAX_DEVICES = 64;
+constexpr int PYOTF_MAX_PEERS = 16;
 inline int current_device_slot() {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -95,6 +96,13 @@ struct pyotf_pr {
     void* dtab = nullptr;           // [nz][dtab_size] defocus tables of this stack (built once)
     void* state = nullptr;          // PrState
     cudaStream_t stream = nullptr;  // creation stream: the state's buffers are stream-ordered allocations on it
+    // z-sharded runs: peer-mapped window (CUDA IPC; layout in pr.cuh) into which every rank's finalize kernel pushes
+    // its partial sums over NVLink
+    void* win = nullptr;            // this rank's window (cudaMalloc, exported)
+    size_t win_bytes = 0;
+    void* peer[pyotf::PYOTF_MAX_PEERS] = {};   // every rank's window as mapped here (peer[win_rank] == win)
+    int win_rank = 0, win_world = 0, win_alloc_world = 0;
+    long long epoch_base = 0;       // epochs are monotonic over the life of the window
     int* h_flags = nullptr;         // pinned: early-stop polling
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

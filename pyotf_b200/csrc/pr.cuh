@@ -292,6 +292,44 @@ __global__ void pr_reduce_kernel(const cplx<T>* __restrict__ partial, const doub
     }
 }
 
+// Window of one rank (peer-mapped by every other rank), z-sharded runs:
+//   [2 slots][world][KK + nblk] records of 2 x 16 bytes; entry [slot][r] is WRITTEN BY RANK r (posted stores over NVLink):
+//   its partial pupil sums (one record per pixel: re, im), then one copy of its squared-error sum per finalize CTA.
+// Every 16-byte word carries one double as {lo32, flag, hi32, flag} with flag = the iteration's epoch, so each 8-byte
+// half validates itself: the reader spins on the word until both flags match -- no fence, no separate ready flag,
+// no round trip (the low-latency protocol of collective libraries).  A rank publishes into every window, its own
+// included; every rank then polls and reads only its own local window.
+__host__ __device__ __forceinline__ size_t pr_win_bytes(int KK, int nblk, int world) { return (size_t)32 * 2 * world * (KK + nblk); }
+__host__ __device__ __forceinline__ uint4* pr_win_rec(void* win, int KK, int nblk, int world, int slot, int r) {
+    return reinterpret_cast<uint4*>(win) + 2 * ((size_t)slot * world + r) * (KK + nblk);      // two words per record
+}
+__device__ __forceinline__ void ll_store(uint4* dst, double v, unsigned flag) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+// spins until the word carries `flag` (bounded: false after ~20 s, a peer died)
+__device__ __forceinline__ bool ll_load(const uint4* src, unsigned flag, double& v) {
+    unsigned long long t0 = 0;
+    for (unsigned spin = 0;; ++spin) {
+        unsigned a, b, c, d;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
+        if (b == flag && d == flag) { v = __hiloint2double((int)c, (int)a); return true; }
+        if ((spin & 1023u) == 1023u) {
+            unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t0 == 0) t0 = t1;
+            else if (t1 - t0 > 20000000000ull) return false;
+        }
+    }
+}
+
+struct PrPeers {
+    int world;                          // 0: no peers (single GPU or NCCL-reduced sums)
+    int rank;
+    int slot;
+    long long epoch;                    // this iteration's flag value (its low 32 bits travel with every word)
+    void* win[PYOTF_MAX_PEERS];         // every rank's window as mapped into this process (fixed rank order)
+};
+
 struct PrFinalArgs {
     int iter, K, nparts;
     int nmse;               // entries of mse_part (one per CTA of the kernel that compared model and data)
@@ -419,6 +457,120 @@ __global__ void __launch_bounds__(256) pr_finalize_kernel(PrFinalArgs a, const T
         if (tid == 0) {
             double* dp = diffpart + (size_t)((a.iter + 1) & 1) * 2 * gridDim.x;
             dp[2 * blockIdx.x] = num; dp[2 * blockIdx.x + 1] = den;
+        }
+    }
+}
+
+
+// pr_finalize_kernel for z-sharded runs, fused with the sum over ranks: CTA b sums this rank's partial pupils for
+// its 32 pixels and stores the result (and this rank's squared-error sum) into entry [rank] of EVERY rank's window --
+// posted writes over NVLink, nobody waits for a round trip.  It then reads the entries of CTA b of every rank from
+// its OWN window (spinning on the self-validating words, local memory) and adds them in rank order, so all
+// ranks compute bit-identical pupils and scalars and take identical stop decisions: the all-reduce of the
+// reference-less multi-GPU loop without a collective call or an extra launch.
+template <typename T>
+__global__ void __launch_bounds__(256) pr_finalize_peers_kernel(PrFinalArgs a, PrPeers peers, const cplx<T>* __restrict__ partial,
+                                                                const double* __restrict__ mse_part,
+                                                                const unsigned char* __restrict__ mask,
+                                                                cplx<T>* __restrict__ pupil0, cplx<T>* __restrict__ pupil1,
+                                                                double* __restrict__ diffpart /* [2][nblk][2] */,
+                                                                double* __restrict__ mse, double* __restrict__ mse_diff,
+                                                                double* __restrict__ pupil_diff, PrState* __restrict__ state) {
+    __shared__ double2 red[PR_FIN_LANES][PR_FIN_PIX];
+    const int tid = threadIdx.x;
+    const int px = tid & (PR_FIN_PIX - 1), lane = tid / PR_FIN_PIX;
+    const int KK = a.K * a.K, nblk = gridDim.x, W = peers.world;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (state->stopped) return;
+    const int p = blockIdx.x * PR_FIN_PIX + px;
+    // ---- this rank's partial sums for the CTA's pixels (16 loads in flight per thread) ----
+    double sx = 0.0, sy = 0.0;
+    if (p < KK) {
+        const cplx<T>* __restrict__ pp = partial + p;
+        for (int q0 = lane; q0 < a.nparts; q0 += 16 * PR_FIN_LANES) {
+            cplx<T> v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int q = q0 + k * PR_FIN_LANES;
+                v[k] = q < a.nparts ? pp[(size_t)q * KK] : mk<T>(0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { sx += (double)v[k].x; sy += (double)v[k].y; }
+        }
+    }
+    red[lane][px] = make_double2(sx, sy);
+    __syncthreads();
+    if (tid < 32) {
+        const double mse_local = warp_sum_fixed(mse_part, a.nmse, 1, tid);
+        sx = 0.0; sy = 0.0;
+#pragma unroll
+        for (int l = 0; l < PR_FIN_LANES; ++l) { sx += red[l][px].x; sy += red[l][px].y; }
+        // ---- publish into every rank's window (self-validating words: no fence, no flag) ----
+        const unsigned flag = (unsigned)peers.epoch;
+        for (int r = 0; r < W; ++r) {
+            uint4* dst = pr_win_rec(peers.win[r], KK, nblk, W, peers.slot, peers.rank);
+            if (p < KK) { ll_store(dst + 2 * p, sx, flag); ll_store(dst + 2 * p + 1, sy, flag); }
+            if (tid == 0) ll_store(dst + 2 * (KK + blockIdx.x), mse_local, flag);
+        }
+        // ---- sums over ranks, fixed order; every rank reads the same stored doubles from its own window ----
+        void* const mine = peers.win[peers.rank];
+        double msum = 0.0;
+        bool ok = true;
+        sx = 0.0; sy = 0.0;
+        for (int r = 0; r < W; ++r) {
+            const uint4* src = pr_win_rec(mine, KK, nblk, W, peers.slot, r);
+            double m, vx = 0.0, vy = 0.0;
+            ok &= ll_load(src + 2 * (KK + blockIdx.x), flag, m);
+            if (p < KK) { ok &= ll_load(src + 2 * p, flag, vx); ok &= ll_load(src + 2 * p + 1, flag, vy); }
+            msum += m; sx += vx; sy += vy;
+        }
+        if (!__all_sync(0xffffffffu, ok)) { if (tid == 0) state->stopped = 2; return; }
+        // ---- scalars and the stop test: identical on every CTA of every rank ----
+        const double new_mse = msum / a.npix_total;
+        double md = nan(""), pd = nan("");
+        if (a.iter > 0) {
+            const double old_mse = mse[a.iter - 1];
+            md = fabs(old_mse - new_mse) / old_mse;                    // phaseretrieval.py:103
+            const double* dp = diffpart + (size_t)(a.iter & 1) * 2 * gridDim.x;
+            const double num = warp_sum_fixed(dp, gridDim.x, 2, tid);
+            const double den = warp_sum_fixed(dp + 1, gridDim.x, 2, tid);
+            pd = num / den;                                            // :105
+        }
+        const int stop = (pd < a.pupil_tol) || (md < a.mse_tol) || (new_mse < a.mse_tol);   // :114
+        if (tid == 0 && blockIdx.x == 0 && *reinterpret_cast<volatile int*>(&state->stopped) == 0) {
+            mse[a.iter] = new_mse; mse_diff[a.iter] = md; pupil_diff[a.iter] = pd;
+            state->iters_run = a.iter + 1;
+            if (stop) { state->final_is_next = 0; state->stopped = 1; }
+            else if (a.last_iter) state->final_is_next = 1;
+        }
+        if (!stop) {
+            const cplx<T>* __restrict__ oldp = a.cur ? pupil1 : pupil0;
+            cplx<T>* __restrict__ newp = a.cur ? pupil0 : pupil1;
+            double num = 0.0, den = 0.0;
+            if (p < KK) {
+                const double m = mask[p] ? 1.0 : 0.0;
+                sx = sx / a.nz_total * m; sy = sy / a.nz_total * m;        // mean(0) * mask   :127
+                if (a.phase_only) {                                        // exp(i angle(.)) * mask   :130
+                    const double mag = hypot(sx, sy);
+                    if (mag > 0.0) { sx = sx / mag * m; sy = sy / mag * m; }
+                    else { sx = m; sy = 0.0; }
+                }
+                const cplx<T> o = oldp[p];
+                const cplx<T> nv = mk<T>((T)sx, (T)sy);
+                newp[p] = nv;
+                const double dx = (double)o.x - (double)nv.x, dy = (double)o.y - (double)nv.y;
+                num = dx * dx + dy * dy;
+                den = (double)o.x * (double)o.x + (double)o.y * (double)o.y;
+            }
+            for (int o = 16; o; o >>= 1) {
+                num += __shfl_xor_sync(0xffffffffu, num, o);
+                den += __shfl_xor_sync(0xffffffffu, den, o);
+            }
+            if (tid == 0) {
+                double* dp = diffpart + (size_t)((a.iter + 1) & 1) * 2 * gridDim.x;
+                dp[2 * blockIdx.x] = num; dp[2 * blockIdx.x + 1] = den;
+            }
         }
     }
 }

@@ -222,6 +222,18 @@ template <typename T> int pr_generic_passes(pyotf_pr* s, int cur, cudaStream_t s
 
 int comm_allreduce_f64(pyotf_comm* c, double* buf, long long n, cudaStream_t st);
 
+template <class K, class... A>
+int pr_launch(bool pdl, K kern, dim3 grid, dim3 block, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    PYOTF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, args...));
+    return 0;
+}
+
 template <typename T>
 int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int phase_only, pyotf_comm* comm,
            double* mse_host, double* mse_diff_host, double* pupil_diff_host, int* iters_run_host, cudaStream_t st) {
@@ -249,7 +261,12 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
     int launched = 0;
     // programmatic dependent launch for the single-GPU fused loop (kernels overlap their neighbours' tails)
     static const bool no_pdl = getenv("PYOTF_B200_NO_PDL") != nullptr;
-    const bool use_pdl = !comm && !s->generic && !no_pdl;
+    // z-sharded: with a peer window (pyotf_b200_pr_window_*) the cross-rank sum happens inside the finalize kernel
+    // over NVLink and the loop keeps its programmatic launches; without one it falls back to an NCCL all-reduce
+    const bool window = comm && s->win && s->win_world >= 1;
+    const bool use_pdl = (!comm || window) && !s->generic && !no_pdl;
+    PrPeers peers = {};
+    if (window) { peers.world = s->win_world; peers.rank = s->win_rank; for (int r = 0; r < s->win_world; ++r) peers.win[r] = s->peer[r]; }
     for (int i = 0; i < max_iters; ++i) {
         if (i % CHK == 0 && i >= 2 * CHK) {            // stay at most ~2*CHK iterations ahead of the device
             const int slot = (i / CHK - 2) % NSLOT;
@@ -260,7 +277,15 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
         int rc = s->generic ? pr_generic_passes<T>(s, cur, st) : pr_plane_launch<T>(s, cur, use_pdl, st);
         if (rc) return rc;
         fa.iter = i; fa.cur = cur; fa.last_iter = i == max_iters - 1; fa.nmse = s->nmse;
-        if (comm) {
+        if (window) {
+            peers.slot = i & 1; peers.epoch = s->epoch_base + i + 1;
+            fa.nparts = s->nparts;
+            rc = pr_launch(use_pdl, pr_finalize_peers_kernel<T>, dim3((unsigned)s->nblk), dim3(256), st, fa, peers,
+                           (const cplx<T>*)s->partial, (const double*)s->mse_part, (const unsigned char*)h->maskc,
+                           (cplx<T>*)s->pupil[0], (cplx<T>*)s->pupil[1], s->diffpart, s->mse, s->mse_diff, s->pupil_diff,
+                           (PrState*)s->state);
+            if (rc) return rc;
+        } else if (comm) {
             pr_reduce_kernel<T><<<(KK + 1 + 255) / 256, 256, 0, st>>>((const cplx<T>*)s->partial, s->mse_part, s->nparts, s->nmse, KK,
                                                                      (double2*)s->sums, (const PrState*)s->state);
             PYOTF_CUDA_OK(cudaGetLastError());
@@ -302,6 +327,8 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
     PYOTF_CUDA_OK(cudaMemcpyAsync(&hs, s->state, sizeof(PrState), cudaMemcpyDeviceToHost, st));
     PYOTF_CUDA_OK(cudaStreamSynchronize(st));
     const int n = hs.iters_run;
+    if (window) s->epoch_base += max_iters;            // the same on every rank, whatever was enqueued after a stop
+    PYOTF_REQUIRE(hs.stopped != 2, "pr_run: a peer rank did not publish its partial sums in time (z-sharded run)");
     PYOTF_REQUIRE(n >= 1 && n <= launched, "pr_run: inconsistent device state");
     s->applied = (start + n - 1) & 1;                  // the pupil iteration n-1 applied   (result.model)
     s->cur = hs.stopped ? s->applied : (s->applied ^ 1);   // final new_pupil                  :144-148

@@ -516,3 +516,15 @@ def apply_named_aberrations(model, aberrations):
     for aberration, magnitude in aberrations.items():
         pcoefs = pcoefs + named_aberration_to_pcoefs(aberration, magnitude)
     return apply_aberration(model, None, pcoefs)
+
+
+def otfi_zsharded(model, nz_total, group=None, mode="auto"):
+    """OTFi of a stack whose planes are sharded over the ranks of a torch.distributed group (one process per GPU):
+    `model` holds this rank's contiguous block of planes (its ``zrange`` slice -- the reference's own shard API,
+    pyotf/otf.py:321-333) and the result is this rank's z block of ``fftshift(fftn(ifftshift(PSFi)))`` over the
+    WHOLE stack (pyotf/otf.py:209-212, pyotf/utils.py:15-17) as a CUDA tensor.  ``mode``: "gather" (all-gather the
+    real PSFi, transform locally), "alltoall" (2D transforms locally, all-to-all transpose, z transform, transpose
+    back) or "auto"; see pyotf_b200/_dist.py."""
+    from . import _dist
+
+    return _dist.otfi_zsharded(model.PSFi_dev, int(nz_total), group=group, mode=mode)

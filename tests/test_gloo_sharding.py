@@ -64,3 +64,35 @@ def test_z_sharded_iteration_matches_unsharded(tmp_path):
     np.testing.assert_allclose(got[:6], o["mse"], rtol=1e-12)
     pupil = got[6:].view(np.complex128).reshape(32, 32)
     assert np.linalg.norm(pupil - o["pupil"]) / np.linalg.norm(o["pupil"]) <= 1e-12
+
+
+def _otfi_worker(rank, world, port, out, mode):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pyotf_b200 import _dist
+    from pyotf_b200._engine import shard_bounds
+
+    z = orc.default_zrange(9, 300)                         # 9 planes over 2 ranks: uneven z blocks (5 + 4)
+    full = orc.psfi(orc.hanser_psfa(OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], 20, z))     # 20 rows: y blocks 10 + 10
+    lo, hi = shard_bounds(9, rank, world)
+    mine = torch.from_numpy(np.ascontiguousarray(full[lo:hi]))
+    got = _dist.otfi_zsharded(mine, 9, mode=mode, fft=_dist.numpy_centred_fft).numpy()
+    np.save(f"{out}.{rank}.npy", got)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("mode", ["gather", "alltoall"])
+def test_z_sharded_otfi_exchange_matches_whole_stack(tmp_path, mode):
+    """OTFi of a z-sharded stack: both exchange schemes of pyotf_b200._dist return every rank's
+    z block of easy_fft(PSFi) (pyotf/otf.py:209-212); the local transforms are numpy here (gloo, CPU), the CUDA
+    kernel on the GPU box (tools/multigpu_check.py)."""
+    out = str(tmp_path / "o")
+    port = 29400 + (os.getpid() + (7 if mode == "gather" else 13)) % 500
+    mp.spawn(_otfi_worker, args=(2, port, out, mode), nprocs=2, join=True)
+    z = orc.default_zrange(9, 300)
+    ref = orc.otfi(orc.psfi(orc.hanser_psfa(OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], 20, z)))
+    got = np.concatenate([np.load(f"{out}.{r}.npy") for r in range(2)])
+    assert got.shape == ref.shape
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-13
