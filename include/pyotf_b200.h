@@ -247,6 +247,17 @@ int pyotf_b200_fftn(const void* in_dev, void* out_dev, int ndim, const long long
 /* out[i] = sum_v |a[v][i]|^2  (BasePSF.PSFi from an existing PSFa, otf.py:204-207) */
 int pyotf_b200_abs2_sum0(const void* a_dev, int nvec, long long n, void* out_dev, int dtype, void* stream);
 
+/* ---- N4: microscope models on the device-resident PSFi (pyotf/microscope.py) ---------------------------------
+ * WidefieldMicroscope.PSF (microscope.py:106-124): np.roll by `shift` along y and x, sum factor x factor lateral
+ * bins (dphtools.utils.bin_ndarray, un-vendored: block sum), optionally divide by the total.
+ *   in [nz][size][size] real -> out [nz][size/factor][size/factor] real (dtype = PYOTF_F32 / PYOTF_F64). */
+int pyotf_b200_bin_lateral(const void* in_dev, int nz, int size, int factor, int shift, void* out_dev, int normalise,
+                           int dtype, void* stream);
+/* ConfocalMicroscope.model_psf (microscope.py:180-187, 213-227): out = fftconvolve(em, disk(radius)[None], "same",
+ * axes=(1, 2)) * exc with disk = (sqrt(i^2 + j^2) < radius) / count on a ceil(2 radius)|1 window; all [nz][size][size]. */
+int pyotf_b200_disk_conv_mul(const void* em_dev, const void* exc_dev, int nz, int size, double radius, void* out_dev,
+                             int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -375,3 +375,111 @@ def sheppard_otfa(wl, na, ni, res, size, zres, zsize, vec_corr="none", condition
 def sheppard_psfa(otfa):
     """Centered 3D inverse FFT of the shell (otf.py:589-592)."""
     return easy_ifft(otfa, axes=(1, 2, 3))
+
+
+# ----------------------------------------------------------------------------------------------
+# N4: microscope models (pyotf/microscope.py) -- restated for the widefield and the confocal microscope
+# ----------------------------------------------------------------------------------------------
+def bin_ndarray(a, bin_size):
+    """dphtools.utils.bin_ndarray (un-vendored dependency, pyotf/microscope.py:24) with its default operation: the
+    sum over bin_size blocks along every axis."""
+    a = np.asarray(a)
+    shape = []
+    for n, b in zip(a.shape, bin_size):
+        assert n % b == 0
+        shape += [n // b, b]
+    return a.reshape(shape).sum(axis=tuple(range(1, 2 * a.ndim, 2)))
+
+
+def widefield_psf(model_psf, oversample_factor, oversampled_size):
+    """WidefieldMicroscope.PSF (pyotf/microscope.py:106-124)."""
+    psf = model_psf
+    if oversample_factor > 1:
+        if oversampled_size % 2 == 0:
+            shift = oversample_factor // 2
+            psf = np.roll(psf, (shift, shift), axis=(1, 2))
+        psf = bin_ndarray(psf, (1, oversample_factor, oversample_factor))
+    return psf / psf.sum()
+
+
+def disk_kernel(radius):
+    """_disk_kernel (pyotf/microscope.py:180-187)."""
+    full_size = int(np.ceil(radius * 2))
+    if full_size % 2 == 0:
+        full_size += 1
+    coords = np.indices((full_size, full_size)) - (full_size - 1) // 2
+    r = np.sqrt((coords ** 2).sum(0))
+    kernel = r < radius
+    return kernel / kernel.sum()
+
+
+def confocal_model_psf(psf_em, psf_exc, wl, na, res, pinhole_size):
+    """ConfocalMicroscope.model_psf (pyotf/microscope.py:213-227)."""
+    from scipy.signal import fftconvolve
+
+    airy_unit = 1.22 * wl / na / res
+    pixel_pinhole_radius = pinhole_size * airy_unit / 2
+    if pixel_pinhole_radius > 1.5:
+        psf_det = fftconvolve(psf_em, disk_kernel(pixel_pinhole_radius)[None], "same", axes=(1, 2))
+    else:
+        psf_det = psf_em
+    return psf_det * psf_exc
+
+
+# ----------------------------------------------------------------------------------------------
+# N3: data preparation (pyotf/utils.py:76-147, 161-201)
+# ----------------------------------------------------------------------------------------------
+def center_data(data):
+    """pyotf/utils.py:76-124: roll the maximum to the central index of every axis."""
+    centered = data.copy()
+    max_loc = np.unravel_index(data.argmax(), data.shape)
+    for i, (x0, nx) in enumerate(zip(max_loc, data.shape)):
+        centered = np.roll(centered, nx // 2 - x0, i)
+    return centered
+
+
+def remove_bg(data, multiplier):
+    """pyotf/utils.py:127-147: subtract multiplier x the mode of an unsigned integer array."""
+    if not np.issubdtype(data.dtype, np.integer):
+        raise ValueError("Floating point numbers unsupported")
+    if np.any(data < 0):
+        raise ValueError("Negative values unsupported")
+    mode = np.bincount(data.ravel()).argmax()
+    return data - multiplier * float(mode)
+
+
+def _fft_pad_constant(data, newshape):
+    """Stand-in for dphtools.utils.fft_pad(mode="constant") (un-vendored; PARITY UNPINNED): zero padding that keeps the
+    element at index n // 2 of every axis at index new_n // 2."""
+    pads = []
+    for n, m in zip(data.shape, newshape):
+        before = m // 2 - n // 2
+        pads.append((before, m - n - before))
+    return np.pad(data, pads, mode="constant")
+
+
+def _slice_maker(centers, width):
+    """Stand-in for dphtools.utils.slice_maker (un-vendored; PARITY UNPINNED): start = centre - width // 2 clipped at 0,
+    stop = start + width."""
+    out = []
+    for c in centers:
+        lo = max(int(c) - int(width) // 2, 0)
+        out.append(slice(lo, lo + int(width)))
+    return tuple(out)
+
+
+def prep_data_for_pr(data, xysize=None, multiplier=1.05):
+    """pyotf/utils.py:161-201.  The no-resize branch (xysize == ny == nx: BASELINE config 2) is pinned to the live
+    reference; the pad / crop branches go through the two dphtools stand-ins above and are unpinned."""
+    nz, ny, nx = data.shape
+    data_without_bg = remove_bg(data, multiplier)
+    if xysize is None:
+        xysize = max(ny, nx)
+    if xysize == ny == nx:
+        pad_data = data_without_bg
+    elif xysize >= max(ny, nx):
+        pad_data = _fft_pad_constant(data_without_bg, (nz, xysize, xysize))
+    else:
+        my_slice = _slice_maker(((ny + 1) // 2, (nx + 1) // 2), xysize)
+        pad_data = center_data(data_without_bg)[(Ellipsis,) + my_slice]
+    return np.fmax(0, pad_data)

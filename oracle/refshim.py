@@ -50,8 +50,22 @@ def _stub_modules():
     def _unavailable(*a, **k):
         raise NotImplementedError("dphtools is not installed; stubbed by oracle/refshim.py")
 
-    for fn in ("fft_pad", "slice_maker", "bin_ndarray", "radial_profile"):
+    for fn in ("fft_pad", "slice_maker", "radial_profile"):
         setattr(dph_utils, fn, _unavailable)
+
+    def bin_ndarray(ndarray, new_shape=None, bin_size=None, operation="sum"):
+        """Stand-in for dphtools.utils.bin_ndarray with its default operation (block sum); the only caller on a
+        tested path, WidefieldMicroscope.PSF (pyotf/microscope.py:121), normalises the result, so a block mean
+        would give the same answer."""
+        import numpy as np
+
+        assert new_shape is None and operation == "sum"
+        shape = []
+        for n, b in zip(ndarray.shape, bin_size):
+            shape += [n // b, b]
+        return np.asarray(ndarray).reshape(shape).sum(axis=tuple(range(1, 2 * ndarray.ndim, 2)))
+
+    dph_utils.bin_ndarray = bin_ndarray
     dph.utils = dph_utils
     stubs["dphtools"] = dph
     stubs["dphtools.utils"] = dph_utils
@@ -75,7 +89,7 @@ def load_reference():
     sys.path.insert(0, REFERENCE_ROOT)
     try:
         pkg = importlib.import_module("pyotf")
-        for sub in ("utils", "zernike", "otf", "phaseretrieval"):
+        for sub in ("utils", "zernike", "otf", "phaseretrieval", "microscope"):
             importlib.import_module(f"pyotf.{sub}")
     finally:
         sys.path.remove(REFERENCE_ROOT)

@@ -54,6 +54,8 @@ PROTOTYPES = {
     "pyotf_b200_zernike_gram": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
     "pyotf_b200_fftn": (_i, [_vp, _vp, _i, C.POINTER(_ll), _ip, _i, _i, _i, _i, _i, _i, _vp]),
     "pyotf_b200_abs2_sum0": (_i, [_vp, _i, _ll, _vp, _i, _vp]),
+    "pyotf_b200_bin_lateral": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "pyotf_b200_disk_conv_mul": (_i, [_vp, _vp, _i, _i, _d, _vp, _i, _vp]),
     "pyotf_b200_hanser_aberration_pupil": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "pyotf_b200_sheppard_otfa": (_i, [C.POINTER(SheppardParams), _vp, _vp, _vp]),
     "pyotf_b200_sheppard_psf": (_i, [C.POINTER(SheppardParams), _vp, _vp, _vp, _vp]),

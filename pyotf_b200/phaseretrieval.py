@@ -59,39 +59,8 @@ def retrieve_phase(data, params, max_iters=200, pupil_tol=1e-8, mse_tol=1e-8, ph
         ``comm`` a ``pyotf_b200._engine.Comm`` (one all-reduce per iteration)
     """
     assert max_iters > 0, "Must have at least one iteration"
-    assert data.shape[1] == data.shape[2], "Data is not square in x/y"
-    assert data.ndim == 3, "Data doesn't have enough dims"
-    params.update(dict(vec_corr="none", condition="none", zsize=data.shape[0], size=data.shape[-1]))
-    model = HanserPSF(**params, precision=precision)
-    model._check_size()   # 32..256 powers of two: fused kernel K2; every other size: the four-pass path K2b
-    torch = _engine._torch()
-    want = torch.float32 if model.precision == "fp32" else torch.float64
-    if not isinstance(data, np.ndarray) and hasattr(data, "is_cuda"):
-        data_dev = data.to(device="cuda", dtype=want)
-    else:
-        a = np.asarray(data)
-        if a.dtype not in (np.float32, np.float64):
-            a = a.astype(np.float64)
-        data_dev = torch.as_tensor(np.ascontiguousarray(a), device="cuda")
-    state = _engine.PRState(model.wl, model.na, model.ni, model.res, model.size, model.zrange, data_dev,
-                            model.precision, nz_total=nz_total, rows_per_cta=rows_per_cta)
-    mse, mse_diff, pupil_diff = state.run(max_iters, pupil_tol, mse_tol, phase_only, comm)
-    if len(mse) == max_iters and not _stopped(mse, mse_diff, pupil_diff, pupil_tol, mse_tol):
-        logger.info("Reach max iterations without convergence")
-    logger.info(
-        f"Finished with {len(mse) - 1} iterations and rmse={np.sqrt(mse[-1]):.2g}, "
-        + f"mse_diff={mse_diff[-1]:.2g}, pupil_diff={pupil_diff[-1]:.2g}"
-    )
-    new_pupil = _engine.to_host(state.get_pupil(applied=False))
-    # the model keeps the pupil it last applied (phaseretrieval.py:97), device resident
-    model.apply_pupil(state.get_pupil(applied=True))
-    model._gen_kr()
-    mask = fftshift((model._kr <= model.na / model.wl).astype(float))
-    phase = unwrap_phase(fftshift(np.angle(new_pupil))) * mask
-    magnitude = fftshift(abs(new_pupil)) * mask
-    result = PhaseRetrievalResult(magnitude, phase, mse, pupil_diff, mse_diff, model)
-    result.pupil = new_pupil  # unshifted complex pupil (extension: no unwrap round trip)
-    return result
+    pr = PhaseRetrieval(data, params, precision=precision, comm=comm, nz_total=nz_total, rows_per_cta=rows_per_cta)
+    return pr.run(max_iters, pupil_tol, mse_tol, phase_only)
 
 
 def _stopped(mse, mse_diff, pupil_diff, pupil_tol, mse_tol):
@@ -100,19 +69,71 @@ def _stopped(mse, mse_diff, pupil_diff, pupil_tol, mse_tol):
 
 
 class PhaseRetrieval:
-    """Object form of ``retrieve_phase`` that keeps the device state between calls.
+    """Object form of ``retrieve_phase`` that keeps the device state (measured stack, defocus tables, pupil
+    estimate) between calls.  Not part of the reference, which only has the function.
 
-    ``PhaseRetrieval(data, params).run(100, 1e-4, 1e-4)`` equals ``retrieve_phase(data, params, 100,
-    1e-4, 1e-4)``; ``step()`` / ``set_pupil()`` expose single iterations (adaptive-optics loops,
-    parity tests).  Not part of the reference (which only has the function).
+    ``PhaseRetrieval(data, params).run(100, 1e-4, 1e-4)`` is ``retrieve_phase(data, params, 100, 1e-4, 1e-4)``.
+    ``set_pupil(pupil)`` re-seeds the estimate (``None``: the ideal pupil the reference starts from,
+    pyotf/phaseretrieval.py:89); ``step(n)`` runs n more iterations of pyotf/phaseretrieval.py:95-130 from the
+    current estimate and returns their ``(mse, mse_diff, pupil_diff)``; ``pupil`` is the current estimate.  ``run``
+    always starts from the ideal pupil, like the function.
     """
 
     def __init__(self, data, params, *, precision=None, comm=None, nz_total=None, rows_per_cta=0):
-        self.data, self.params = data, params
-        self.kwargs = dict(precision=precision, comm=comm, nz_total=nz_total, rows_per_cta=rows_per_cta)
+        assert data.shape[1] == data.shape[2], "Data is not square in x/y"
+        assert data.ndim == 3, "Data doesn't have enough dims"
+        params.update(dict(vec_corr="none", condition="none", zsize=data.shape[0], size=data.shape[-1]))
+        self.params, self.comm = params, comm
+        self.model = model = HanserPSF(**params, precision=precision)
+        model._check_size()   # 32..256 powers of two: fused kernel K2; every other size: the four-pass path K2b
+        torch = _engine._torch()
+        want = torch.float32 if model.precision == "fp32" else torch.float64
+        if not isinstance(data, np.ndarray) and hasattr(data, "is_cuda"):
+            data_dev = data.to(device="cuda", dtype=want)
+        else:
+            a = np.asarray(data)
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            data_dev = torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+        self.state = _engine.PRState(model.wl, model.na, model.ni, model.res, model.size, model.zrange, data_dev,
+                                     model.precision, nz_total=nz_total, rows_per_cta=rows_per_cta)
+
+    def set_pupil(self, pupil=None):
+        """Re-seed the estimate from an unshifted N x N complex pupil (numpy or CUDA tensor); None = ideal pupil."""
+        if pupil is not None and not hasattr(pupil, "is_cuda"):
+            pupil = _engine.to_device_c128(pupil)
+        self.state.set_pupil(pupil)
+
+    @property
+    def pupil(self):
+        """Current pupil estimate, unshifted N x N complex128 (host array)."""
+        return _engine.to_host(self.state.get_pupil(applied=False))
+
+    def step(self, n=1, phase_only=False):
+        """n more iterations from the current estimate, no convergence test; returns (mse, mse_diff, pupil_diff)."""
+        return self.state.run(int(n), 0.0, 0.0, phase_only, self.comm)
 
     def run(self, max_iters=200, pupil_tol=1e-8, mse_tol=1e-8, phase_only=False):
-        return retrieve_phase(self.data, self.params, max_iters, pupil_tol, mse_tol, phase_only, **self.kwargs)
+        assert max_iters > 0, "Must have at least one iteration"
+        state, model = self.state, self.model
+        state.set_pupil(None)
+        mse, mse_diff, pupil_diff = state.run(max_iters, pupil_tol, mse_tol, phase_only, self.comm)
+        if len(mse) == max_iters and not _stopped(mse, mse_diff, pupil_diff, pupil_tol, mse_tol):
+            logger.info("Reach max iterations without convergence")
+        logger.info(
+            f"Finished with {len(mse) - 1} iterations and rmse={np.sqrt(mse[-1]):.2g}, "
+            + f"mse_diff={mse_diff[-1]:.2g}, pupil_diff={pupil_diff[-1]:.2g}"
+        )
+        new_pupil = _engine.to_host(state.get_pupil(applied=False))
+        # the model keeps the pupil it last applied (phaseretrieval.py:97), device resident
+        model.apply_pupil(state.get_pupil(applied=True))
+        model._gen_kr()
+        mask = fftshift((model._kr <= model.na / model.wl).astype(float))
+        phase = unwrap_phase(fftshift(np.angle(new_pupil))) * mask
+        magnitude = fftshift(abs(new_pupil)) * mask
+        result = PhaseRetrievalResult(magnitude, phase, mse, pupil_diff, mse_diff, model)
+        result.pupil = new_pupil  # unshifted complex pupil (extension: no unwrap round trip)
+        return result
 
 
 class PhaseRetrievalResult(object):

@@ -119,3 +119,41 @@ def test_sheppard_equal_res(ref):
     kw = dict(wl=500, na=0.85, ni=1.0, res=140, size=32, zres=140, zsize=32)
     m = ref.otf.SheppardPSF(**kw)
     np.testing.assert_array_equal(orc.sheppard_otfa(**kw), m.OTFa)
+
+
+@pytest.mark.parametrize("size,oversample", [(16, 3), (15, 3), (12, 1), (10, 5)])
+def test_microscope_widefield_and_confocal(size, oversample):
+    """N4: the oracle's restatement of WidefieldMicroscope.PSF / ConfocalMicroscope.model_psf against the live
+    pyotf.microscope (bin_ndarray = block sum, the un-vendored dphtools default, oracle/refshim.py)."""
+    refshim.load_reference()
+    from pyotf import microscope as rm
+
+    kw = dict(model="hanser", na=0.85, ni=1.0, wl=520, size=size, pixel_size=130, oversample_factor=oversample)
+    w = rm.WidefieldMicroscope(**kw)
+    np.testing.assert_array_equal(orc.widefield_psf(w.model.PSFi, oversample, size * oversample), w.PSF)
+    for pinhole in (1.0, 0.05):                       # with and without the pinhole convolution (radius <= 1.5 px)
+        c = rm.ConfocalMicroscope(wl_exc=488.0, pinhole_size=pinhole, **kw)
+        got = orc.confocal_model_psf(c.model.PSFi, c.model_exc.PSFi, 520, 0.85, c.model.res, pinhole)
+        np.testing.assert_array_equal(got, c.model_psf)
+        np.testing.assert_array_equal(orc.widefield_psf(got, oversample, size * oversample), c.PSF)
+        np.testing.assert_array_equal(orc.otfi(c.PSF), c.OTF)
+
+
+def test_data_prep_restatements(ref):
+    """N3: center_data / remove_bg / prep_data_for_PR (no-resize branch) of the oracle against the live
+    pyotf.utils (pyotf/utils.py:76-147, 161-201) and its doctest values (utils.py:91-114, :134-136)."""
+    rng = np.random.default_rng(2)
+    for shape in ((3, 3), (3, 4), (5, 6, 7), (4, 9)):
+        a = rng.integers(0, 50, shape)
+        np.testing.assert_array_equal(orc.center_data(a), ref.utils.center_data(a))
+    np.testing.assert_array_equal(orc.center_data(np.array(((2, 1, 0, 0), (1, 0, 0, 0), (0, 0, 0, 1)))),
+                                  [[0, 1, 0, 0], [0, 0, 2, 1], [0, 0, 1, 0]])
+    np.testing.assert_array_equal(orc.remove_bg(np.array([1, 1, 1, 0, 2]), 1), [0, 0, 0, -1, 1])
+    stack = (rng.poisson(200, (6, 16, 16)) + 100).astype(np.uint16)
+    np.testing.assert_array_equal(orc.remove_bg(stack, 1.1), ref.utils.remove_bg(stack, 1.1))
+    for xysize in (None, 16):
+        np.testing.assert_array_equal(orc.prep_data_for_pr(stack, xysize, 1.1), ref.utils.prep_data_for_PR(stack, xysize, 1.1))
+    with pytest.raises(ValueError):
+        orc.remove_bg(stack.astype(float), 1.0)
+    raw = refshim.read_fixture_stack()
+    np.testing.assert_array_equal(orc.prep_data_for_pr(raw, 256, 1.1), ref.utils.prep_data_for_PR(raw, 256, 1.1))

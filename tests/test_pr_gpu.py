@@ -289,3 +289,30 @@ def test_stack_length_edge_cases(size, nz):
         r = retrieve_phase(data, dict(params), 5, 0, 0, precision=precision)
         assert rel_l2(r.mse, o["mse"]) <= tol
         assert rel_l2(r.pupil, o["pupil"]) <= 2 * tol
+
+
+def test_phase_retrieval_object_keeps_state_step_and_set_pupil():
+    """PhaseRetrieval (object form): run() == retrieve_phase(); step(n) continues from the current estimate, so
+    5 + 7 single-launch steps equal one 12-iteration run; set_pupil() re-seeds the estimate."""
+    from pyotf_b200.otf import HanserPSF, apply_aberration
+    from pyotf_b200.phaseretrieval import PhaseRetrieval, retrieve_phase
+
+    z = (np.arange(6) - 3) * 250.0 + 40.0
+    m = HanserPSF(520, 0.85, 1.0, 130, 64, zrange=z, vec_corr="none", condition="none", precision="fp64")
+    data = apply_aberration(m, None, np.array([0, 0, 0, 0, 0.3, 0.2, -0.4, 0.1])).PSFi * 1e4
+    params = dict(wl=520, na=0.85, ni=1.0, res=130, zrange=z)
+    full = retrieve_phase(data, dict(params), 12, 0, 0, precision="fp64")
+    pr = PhaseRetrieval(data, dict(params), precision="fp64")
+    r = pr.run(12, 0, 0)
+    np.testing.assert_array_equal(r.mse, full.mse)
+    np.testing.assert_array_equal(r.pupil, full.pupil)
+    pr.set_pupil(None)
+    a = pr.step(5)[0]
+    b = pr.step(7)[0]
+    np.testing.assert_allclose(np.concatenate([a, b]), full.mse, rtol=1e-13)
+    np.testing.assert_allclose(pr.pupil, full.pupil, rtol=0, atol=1e-13 * abs(full.pupil).max())
+    # re-seeding with the retrieved pupil reproduces the continuation
+    pr.set_pupil(full.pupil)
+    c = pr.step(1)[0]
+    more = retrieve_phase(data, dict(params), 13, 0, 0, precision="fp64")
+    assert abs(c[0] / more.mse[12] - 1) <= 1e-10

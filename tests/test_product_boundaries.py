@@ -111,7 +111,7 @@ def test_host_unwrap_and_shard_bounds():
         assert sizes == [len(c) for c in np.array_split(np.arange(n), w)]
 
 
-def test_host_unwrap_matches_plain_restatement():
+def test_host_unwrap_matches_plain_restatement_unpinned_vs_skimage():
     """The optimised host unwrap (zero-reliability edges joined as they are generated, all-zero row bands skipped,
     radix sort) against the plain all-edges / stable-sort / union-find restatement in oracle/unwrap_oracle.py:
     identical arrays on pupil-like (zero outside an aperture), dense, noisy, flat and tiny inputs."""
