@@ -185,8 +185,36 @@ template <int DIR, typename T> __device__ __forceinline__ void fft16_mid0(cplx<T
     }
 }
 
+// multiply by e^{DIR * 2 pi i * k / 32}, k compile-time in 0..15
+template <int DIR, int K, typename T> __device__ __forceinline__ cplx<T> mul_w32(cplx<T> a) {
+    if constexpr (K % 2 == 0) return mul_w16<DIR, K / 2>(a);
+    else {
+        // cos / sin of k * 11.25 deg for odd k = 1 .. 15
+        constexpr double C[8] = {0.98078528040323044913, 0.83146961230254523708, 0.55557023301960222474, 0.19509032201612826785,
+                                 -0.19509032201612826785, -0.55557023301960222474, -0.83146961230254523708, -0.98078528040323044913};
+        constexpr double S[8] = {0.19509032201612826785, 0.55557023301960222474, 0.83146961230254523708, 0.98078528040323044913,
+                                 0.98078528040323044913, 0.83146961230254523708, 0.55557023301960222474, 0.19509032201612826785};
+        const T cc = (T)C[K / 2], ss = (T)(DIR > 0 ? S[K / 2] : -S[K / 2]);
+        return mk<T>(a.x * cc - a.y * ss, a.x * ss + a.y * cc);
+    }
+}
+
+// radix-32 as two radix-16 transforms of the even / odd inputs, natural order in/out
+template <int DIR, typename T> __device__ __forceinline__ void fft32(cplx<T>* x) {
+    cplx<T> e[16], o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { e[i] = x[2 * i]; o[i] = x[2 * i + 1]; }
+    fft16<DIR>(e);
+    fft16<DIR>(o);
+#define PYOTF_W32(K) { const cplx<T> t = mul_w32<DIR, K>(o[K]); x[K] = e[K] + t; x[K + 16] = e[K] - t; }
+    PYOTF_W32(0) PYOTF_W32(1) PYOTF_W32(2) PYOTF_W32(3) PYOTF_W32(4) PYOTF_W32(5) PYOTF_W32(6) PYOTF_W32(7)
+    PYOTF_W32(8) PYOTF_W32(9) PYOTF_W32(10) PYOTF_W32(11) PYOTF_W32(12) PYOTF_W32(13) PYOTF_W32(14) PYOTF_W32(15)
+#undef PYOTF_W32
+}
+
 template <int DIR, int R, typename T> __device__ __forceinline__ void fft_radix(cplx<T>* x) {
-    static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "radix");
+    static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16 || R == 32, "radix");
+    if constexpr (R == 32) fft32<DIR>(x);
     if constexpr (R == 2) fft2<DIR>(x[0], x[1]);
     if constexpr (R == 4) fft4<DIR>(x[0], x[1], x[2], x[3]);
     if constexpr (R == 8) fft8<DIR>(x);

@@ -1,10 +1,12 @@
 // Host launchers for the axis-pass FFT (instantiated per dtype in fftnd_f32.cu / fftnd_f64.cu).
 #pragma once
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
 #include "common.cuh"
 #include "fftnd.cuh"
+#include "fft_lines_reg.cuh"
 
 namespace pyotf {
 
@@ -39,8 +41,77 @@ int fft_axis_launch_l(const AxisPass& p, const void* src, void* dst, int smem_li
     return fft_axis_launch_ti<DIR, TIN, T, L, POW2, 4>(p, src, dst, need(4), s);
 }
 
+// the generic strided pass as a line functor of the register-resident kernel (fft_lines_reg.cuh):
+// line = outer * n_inner + inner, element l of a line at ((outer * L + l) * n_inner + inner)
+template <typename TIN, typename T> struct AxisFn {
+    struct Line { const TIN* in; cplx<T>* out; bool has; };
+    using Acc = int;
+    static constexpr int LOAD_BATCH = 8;
+    static constexpr bool HAS_EMPTY = true;
+    AxisPass p;
+    const TIN* src;
+    cplx<T>* dst;
+    __device__ __forceinline__ static Acc acc_init() { return 0; }
+    __device__ __forceinline__ void finish(Acc) const {}
+    __device__ __forceinline__ bool skip() const { return false; }
+    __device__ __forceinline__ cplx<T> twiddle(int k) const { return reinterpret_cast<const cplx<T>*>(p.tw)[k]; }
+    __device__ __forceinline__ Line info(long long line) const {
+        const long long outer = line / p.n_inner, inner = line - outer * p.n_inner;
+        const size_t base = (size_t)outer * p.L * p.n_inner + inner;
+        Line d;
+        d.in = src + base; d.out = dst + base;
+        d.has = p.line_flags ? p.line_flags[line] != 0 : true;
+        return d;
+    }
+    __device__ __forceinline__ bool empty(const Line& d) const { return !d.has; }
+    __device__ __forceinline__ void zero_fill(const Line& d, int o) const {
+        if ((const void*)src != (const void*)dst) d.out[(size_t)o * p.n_inner] = mk<T>(0, 0);
+    }
+    __device__ __forceinline__ cplx<T> load(const Line& d, int i) const {
+        if (!d.has) return mk<T>(0, 0);
+        int l = i + p.in_shift; if (l >= p.L) l -= p.L;              // x_in[i] = src[(i + in_shift) % L]
+        return load_as_cplx<TIN, T>(d.in, (size_t)l * p.n_inner);
+    }
+    __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v, Acc&) const {
+        int l = o + p.out_shift; if (l >= p.L) l -= p.L;             // dst[(o + out_shift) % L] = X[o]
+        d.out[(size_t)l * p.n_inner] = cscale(v, (T)p.scale);
+    }
+};
+
+template <int DIR, typename TIN, typename T, int L>
+int fft_axis_reg_launch(const AxisPass& p, const void* src, void* dst, cudaStream_t s) {
+    AxisFn<TIN, T> f;
+    f.p = p; f.src = (const TIN*)src; f.dst = (cplx<T>*)dst;
+    constexpr size_t smem = fft_lines_reg_smem<T, L>();
+    auto kern = fft_lines_reg_kernel<DIR, T, L, AxisFn<TIN, T>>;
+    static thread_local bool configured[PYOTF_MAX_DEVICES] = {};
+    const int dev_slot = current_device_slot();
+    if (!configured[dev_slot]) {
+        PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev_slot] = true;
+    }
+    const long long nlines = p.n_outer * p.n_inner, nblocks = nlines / RegPlan<L>::LANES;
+    PYOTF_REQUIRE(nblocks > 0 && nblocks < (1ll << 31), "fft: bad grid");
+    kern<<<(unsigned)nblocks, RegPlan<L>::NT, smem, s>>>(nlines, f);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <int DIR, typename TIN, typename T>
 int fft_axis_launch(const AxisPass& p, const void* src, void* dst, int smem_limit, cudaStream_t s) {
+    // strided axes: one lane per line, registers + one exchange (in place is safe: a block reads all of its lines
+    // before it writes any)
+    static const bool no_reg = getenv("PYOTF_B200_NO_REG_LINES") != nullptr;
+    if (!no_reg && p.n_inner > 1) {
+        if (p.L == 64 && p.n_inner % 32 == 0) return fft_axis_reg_launch<DIR, TIN, T, 64>(p, src, dst, s);
+        if (p.L == 128 && p.n_inner % 32 == 0) return fft_axis_reg_launch<DIR, TIN, T, 128>(p, src, dst, s);
+        if (p.L == 256 && p.n_inner % 32 == 0 && fft_lines_reg_smem<T, 256>() <= (size_t)smem_limit)
+            return fft_axis_reg_launch<DIR, TIN, T, 256>(p, src, dst, s);
+        if (p.L == 512 && p.n_inner % 16 == 0 && fft_lines_reg_smem<T, 512>() <= (size_t)smem_limit)
+            return fft_axis_reg_launch<DIR, TIN, T, 512>(p, src, dst, s);
+        if (p.L == 1024 && p.n_inner % 16 == 0 && fft_lines_reg_smem<T, 1024>() <= (size_t)smem_limit)
+            return fft_axis_reg_launch<DIR, TIN, T, 1024>(p, src, dst, s);
+    }
     switch (p.L) {
 #define PYOTF_CASE(LL) case LL: return fft_axis_launch_l<DIR, TIN, T, LL, true>(p, src, dst, smem_limit, s);
         PYOTF_CASE(2) PYOTF_CASE(4) PYOTF_CASE(8) PYOTF_CASE(16) PYOTF_CASE(32) PYOTF_CASE(64) PYOTF_CASE(128)

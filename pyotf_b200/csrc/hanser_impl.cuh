@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "hanser.cuh"
 #include "hanser_big.cuh"
+#include "fft_lines_reg.cuh"
 
 namespace pyotf {
 
@@ -234,8 +235,40 @@ int fft_lines_launch_l(int Lr, long long nlines, F f, int smem_limit, cudaStream
     return fft_lines_launch_ti<DIR, T, L, POW2, LM, 4>(Lr, nlines, f, need(4), s, nblocks_out);
 }
 
+// strided lines (the axis is not contiguous): the register-resident kernel of fft_lines_reg.cuh where a plan exists
+template <int DIR, typename T, int L, class F>
+int fft_lines_reg_launch(long long nlines, F f, cudaStream_t s, int* nblocks_out) {
+    constexpr size_t smem = fft_lines_reg_smem<T, L>();
+    auto kern = fft_lines_reg_kernel<DIR, T, L, F>;
+    static thread_local bool configured[PYOTF_MAX_DEVICES] = {};
+    const int dev_slot = current_device_slot();
+    if (!configured[dev_slot]) {
+        PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev_slot] = true;
+    }
+    const long long nblocks = nlines / RegPlan<L>::LANES;
+    PYOTF_REQUIRE(nblocks > 0 && nblocks < (1ll << 31), "fft: bad grid");
+    if (nblocks_out) *nblocks_out = (int)nblocks;
+    kern<<<(unsigned)nblocks, RegPlan<L>::NT, smem, s>>>(nlines, f);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <int DIR, typename T, bool LM, class F>
 int fft_lines_launch(int L, long long nlines, F f, int smem_limit, cudaStream_t s, int* nblocks_out = nullptr) {
+    if constexpr (!LM) {
+        static const bool no_reg = getenv("PYOTF_B200_NO_REG_LINES") != nullptr;     // A/B knob: the staged kernel
+        if (!no_reg) {
+            if (L == 64 && nlines % 32 == 0) return fft_lines_reg_launch<DIR, T, 64>(nlines, f, s, nblocks_out);
+            if (L == 128 && nlines % 32 == 0) return fft_lines_reg_launch<DIR, T, 128>(nlines, f, s, nblocks_out);
+            if (L == 256 && nlines % 32 == 0 && fft_lines_reg_smem<T, 256>() <= (size_t)smem_limit)
+                return fft_lines_reg_launch<DIR, T, 256>(nlines, f, s, nblocks_out);
+            if (L == 512 && nlines % 16 == 0 && fft_lines_reg_smem<T, 512>() <= (size_t)smem_limit)
+                return fft_lines_reg_launch<DIR, T, 512>(nlines, f, s, nblocks_out);
+            if (L == 1024 && nlines % 16 == 0 && fft_lines_reg_smem<T, 1024>() <= (size_t)smem_limit)
+                return fft_lines_reg_launch<DIR, T, 1024>(nlines, f, s, nblocks_out);
+        }
+    }
     switch (L) {
 #define PYOTF_CASE(LL) case LL: return fft_lines_launch_l<DIR, T, LL, true, LM>(L, nlines, f, smem_limit, s, nblocks_out);
         PYOTF_CASE(2) PYOTF_CASE(4) PYOTF_CASE(8) PYOTF_CASE(16) PYOTF_CASE(32) PYOTF_CASE(64) PYOTF_CASE(128)
