@@ -417,14 +417,15 @@ int hanser_launch_sym256(const HanserArgs<T>& a, int batch, int smem_limit, cuda
 }
 
 template <typename T> int hanser_sym_launch(const HanserArgs<T>& a, int batch, int smem_limit, cudaStream_t s, bool* done) {
+    // one 9-warp group + two store warps per CTA; fp32: two CTAs per SM, so the stores of one plane overlap the
+    // transforms of the next.  (Tuning knobs: PYOTF_B200_K1_SYM_NG=2 = two groups in one CTA per SM (fp32),
+    // PYOTF_B200_K1_SYM_NS=1 = one store warp.)
+    static const int ns = [] { const char* e = getenv("PYOTF_B200_K1_SYM_NS"); return e ? atoi(e) : 2; }();
     if constexpr (sizeof(T) == 4) {
-        // one 9-warp group per CTA, two CTAs per SM: the stores of one plane overlap the transforms of the next
-        // (PYOTF_B200_K1_SYM_NG=2: two groups in one CTA per SM, for comparison)
         static const int ng = [] { const char* e = getenv("PYOTF_B200_K1_SYM_NG"); return e ? atoi(e) : 1; }();
-        static const int ns = [] { const char* e = getenv("PYOTF_B200_K1_SYM_NS"); return e ? atoi(e) : 2; }();
         if (ng == 2) return hanser_launch_sym256<T, 2, 1>(a, batch, smem_limit, s, done);
-        if (ns == 2) return hanser_launch_sym256<T, 1, 2>(a, batch, smem_limit, s, done);
     }
+    if (ns == 2) return hanser_launch_sym256<T, 1, 2>(a, batch, smem_limit, s, done);
     return hanser_launch_sym256<T, 1, 1>(a, batch, smem_limit, s, done);
 }
 
