@@ -203,6 +203,16 @@ int hanser_launch_n(const pyotf_hanser* h, const HanserArgs<T>& a_in, int tabm, 
 // the ideal pupil at N = 256, PSFi only.  *done stays false when the configuration does not fit (caller falls back).
 template <typename T> int hanser_sym_launch(const HanserArgs<T>& a, int batch, int smem_limit, cudaStream_t s, bool* done);
 
+// K1bs (hanser_bigsym.cuh, its own translation units): the same model at N = 1024 (BASELINE config 4), two passes
+// over an L2-resident half-spectrum intermediate.  *done stays false when the configuration does not fit.
+template <typename T>
+int hanser_bigsym_launch(const pyotf_hanser* h, const double* z, int nz, int batch, void* psfi, int smem_limit, cudaStream_t s,
+                         bool* done);
+// K1br: any pupil at N = 1024, PSFi only (same file)
+template <typename T>
+int hanser_biggen_launch(const pyotf_hanser* h, const double* z, int nz, const void* pupilc, int batch, long long pupil_stride,
+                         void* psfi, int smem_limit, cudaStream_t s, bool* done);
+
 // ---------------------------------------------------------------------------------------
 // K1b launchers (hanser_big.cuh): any size, two line-FFT passes per plane chunk
 // ---------------------------------------------------------------------------------------
@@ -426,6 +436,22 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
         case 128: return hanser_launch_n<T, 128>(h, a, tabm, batch, smem_limit, s);
         case 256: return hanser_launch_n<T, 256>(h, a, tabm, batch, smem_limit, s);
         default: break;
+    }
+    if (h->N == 1024 && !pupilc && !psfa && psfi && h->nvec == 1) {
+        static const bool off = getenv("PYOTF_B200_K1BS_OFF") != nullptr;      // A/B knob: the generic two-pass path
+        if (!off) {
+            bool done = false;
+            int rc = hanser_bigsym_launch<T>(h, z, nz, batch, psfi, smem_limit, s, &done);
+            if (rc || done) return rc;
+        }
+    }
+    if (h->N == 1024 && !psfa && psfi) {
+        static const bool off = getenv("PYOTF_B200_K1BR_OFF") != nullptr;      // A/B knob: the staged two-pass path
+        if (!off) {
+            bool done = false;
+            int rc = hanser_biggen_launch<T>(h, z, nz, pupilc, batch, pupil_stride, psfi, smem_limit, s, &done);
+            if (rc || done) return rc;
+        }
     }
     return hanser_launch_big<T>(h, z, nz, pupilc, batch, pupil_stride, psfa, psfi, smem_limit, s);
 }

@@ -43,6 +43,14 @@ def main():
 
     ms = bench._time_gpu(bigstep, reps=6)
     print(f"[{tag} {prec}] hanser 1024^2: {1e3 * ms / 64:8.2f} us / plane  ({64 / ms / 1e3 * 1e3:9.0f} planes/s, {64 * 1024 * 1024 * es / ms / 1e6:7.1f} GB/s)", flush=True)
+    hs, _ = big._handle_and_pupil(None)
+
+    def symstep():
+        st["i"] += 1
+        hs.psf(zc, None, want_psfa=False, want_psfi=True, psfi_out=outb[st["i"] % 2])
+
+    ms = bench._time_gpu(symstep, reps=6)
+    print(f"[{tag} {prec}] hanser 1024^2 default model: {1e3 * ms / 64:8.2f} us / plane  ({64 / ms * 1e3:9.0f} planes/s, {64 * 1024 * 1024 * es / ms / 1e6:7.1f} GB/s)", flush=True)
     del outb
     m = HanserPSF(precision=prec, **bench.CFG1)
     psfi = m.PSFi_dev
