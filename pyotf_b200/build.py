@@ -44,6 +44,28 @@ def _digest():
     return h.hexdigest()
 
 
+def _deps(path, seen=None):
+    """The file and every local header it includes (transitively)."""
+    import re
+
+    seen = set() if seen is None else seen
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(path).read(), flags=re.M):
+        _deps(os.path.normpath(os.path.join(os.path.dirname(path), inc)), seen)
+    return seen
+
+
+def _tu_digest(src):
+    h = hashlib.sha256()
+    for f in sorted(_deps(os.path.join(CSRC, src))):
+        h.update(f.encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(ARCH + FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
     stamp = LIB + ".digest"
     dig = _digest()
@@ -53,6 +75,9 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")
+        tu_stamp, tu_dig = obj + ".digest", _tu_digest(src)
+        if not force and os.path.exists(obj) and os.path.exists(tu_stamp) and open(tu_stamp).read() == tu_dig:
+            return obj                                   # this translation unit and its headers are unchanged
         cmd = [nvcc(), *ARCH, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OBJ, src[:-3] + ".ptxas.log")
@@ -60,6 +85,7 @@ def build(force=False, verbose=False):
         open(log, "w").write("".join(l for l in r.stderr.splitlines(True) if "Compile time" not in l))
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stderr[-4000:]}")
+        open(tu_stamp, "w").write(tu_dig)
         return obj
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:

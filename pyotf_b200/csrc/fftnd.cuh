@@ -23,6 +23,10 @@ struct AxisPass {
     const void* tw;        // [L] e^{+2 pi i k / L} in the transform's dtype (device; cached per length)
     const unsigned char* line_flags;   // optional: one byte per line (outer * n_inner + inner); 0 = the line is
                                        // entirely zero on input, so (in place) it is left untouched
+    int herm_Z = 0, herm_Y = 0;        // last pass of the real 3D transform (contiguous axis only): the source holds
+                                       // the planes kz = 0 .. Z/2 of [kz][y-shifted][x]; line (kz, ys) is stored to the
+                                       // fftshift-ed plane (kz + Z/2) % Z and, for 0 < kz < Z/2, its complex conjugate
+                                       // to the Hermitian partner ((-zs) % Z, (-ys) % Y, (-xs) % X)
 };
 
 // radix sequence for power-of-two L (product == L): up to three stages of radix <= 16
@@ -242,7 +246,19 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
                 const int t = contiguous ? w / L : w % TI, l = contiguous ? w % L : w / TI;
                 int o = l - p.out_shift; if (o < 0) o += L;
                 const int pos = digit_reversed_pos<L>(o);
-                dst[base + t * stride_t + l * stride_l] = cscale(res[(size_t)t * pitch + fft_pad<POW2>(pos)], scale);
+                const cplx<T> v = cscale(res[(size_t)t * pitch + fft_pad<POW2>(pos)], scale);
+                if (p.herm_Z) {
+                    const long long line = outer + t;
+                    const int kz = (int)(line / p.herm_Y), ys = (int)(line - (long long)kz * p.herm_Y), hz = p.herm_Z / 2;
+                    const int zs = kz + hz == p.herm_Z ? 0 : kz + hz;
+                    dst[((size_t)zs * p.herm_Y + ys) * L + l] = v;
+                    if (kz > 0 && kz < hz) {
+                        const int ym = ys ? p.herm_Y - ys : 0, lm = l ? L - l : 0;
+                        dst[((size_t)(p.herm_Z - zs) * p.herm_Y + ym) * L + lm] = cconj(v);
+                    }
+                } else {
+                    dst[base + t * stride_t + l * stride_l] = v;
+                }
             }
             return;
         }
@@ -253,7 +269,19 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
             int o = l - p.out_shift; if (o < 0) o += Lr;
             int pos = o;
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
-            dst[base + t * stride_t + l] = cscale(res[(size_t)t * pitch + fft_pad<POW2>(pos)], scale);
+            const cplx<T> v = cscale(res[(size_t)t * pitch + fft_pad<POW2>(pos)], scale);
+            if (p.herm_Z) {
+                const long long line = outer + t;
+                const int kz = (int)(line / p.herm_Y), ys = (int)(line - (long long)kz * p.herm_Y), hz = p.herm_Z / 2;
+                const int zs = kz + hz == p.herm_Z ? 0 : kz + hz;
+                dst[((size_t)zs * p.herm_Y + ys) * Lr + l] = v;
+                if (kz > 0 && kz < hz) {
+                    const int ym = ys ? p.herm_Y - ys : 0, lm = l ? Lr - l : 0;
+                    dst[((size_t)(p.herm_Z - zs) * p.herm_Y + ym) * Lr + lm] = cconj(v);
+                }
+            } else {
+                dst[base + t * stride_t + l] = v;
+            }
         }
     } else {
         for (int w = threadIdx.x; w < nlines * Lr; w += blockDim.x) {

@@ -149,6 +149,143 @@ template <typename T> int fft_twiddles(int L, const void** out, cudaStream_t s) 
     return 0;
 }
 
+// ---- real 3D forward transform (OTFi = easy_fft(PSFi), pyotf/otf.py:209-212): first pass ---------------------------
+// z-lines of a REAL [Z][Y][X] array -> the planes kz = 0 .. Z/2 of its z-transform (the rest is the complex
+// conjugate mirror, filled in by the last pass).  One lane per PAIR of adjacent columns (x, x + 1): the two real lines
+// travel as one complex line a + i b (one float2 load per sample), and are separated after the transform,
+//     A[kz] = (C[kz] + conj C[-kz]) / 2,   B[kz] = (C[kz] - conj C[-kz]) / 2i,
+// which needs C[kz] and C[Z - kz] in the same thread: second-stage unit c1 is executed together with unit R1 - c1
+// (units 0 and R1/2 pair with themselves).  Same mapping as fft_lines_reg.cuh otherwise: a warp executes one unit
+// for 32 column pairs, all first-stage loads in flight, one shared-memory exchange, 16-byte stores.
+template <typename T, int Z>
+__global__ void __launch_bounds__(16 * RegPlan<Z>::R1) rfft_z_half_kernel(const T* __restrict__ src, cplx<T>* __restrict__ dst,
+                                                                          long long plane, int in_shift, const cplx<T>* __restrict__ twg) {
+    using P = RegPlan<Z>;
+    constexpr int R1 = P::R1, R2 = P::R2, NW = R1 / 2, NT = 32 * NW;
+    using V2 = typename vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);            // [Z]
+    cplx<T>* E = tw + Z;                                            // [R1][R2][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t j = 2 * ((size_t)blockIdx.x * 32 + lane);          // first column of this lane's pair, within a plane
+    for (int k = threadIdx.x; k < Z; k += NT) tw[k] = twg[k];
+    __syncthreads();
+    for (int g = warp; g < R2; g += NW) {
+        cplx<T> x[R1];
+#pragma unroll
+        for (int q = 0; q < R1; ++q) {
+            int zz = R2 * q + g + in_shift; if (zz >= Z) zz -= Z;   // x_in[i] = src[(i + in_shift) % Z]
+            const V2 v = *reinterpret_cast<const V2*>(src + (size_t)zz * plane + j);
+            x[q] = mk<T>(v.x, v.y);
+        }
+        fft_radix<-1, R1>(x);
+        cplx<T>* e = E + (size_t)g * 32 + lane;
+        e[0] = x[0];
+#pragma unroll
+        for (int c = 1; c < R1; ++c) e[(size_t)c * R2 * 32] = cmulc(x[c], tw[(g * c) & (Z - 1)]);
+    }
+    __syncthreads();
+    // A / B at kz from C[kz] = c and C[-kz] = m
+    auto put = [&](int kz, cplx<T> c, cplx<T> m) {
+        if (kz > Z / 2) return;
+        const T h = (T)0.5;
+        const cplx<T> a = mk<T>((c.x + m.x) * h, (c.y - m.y) * h);
+        const cplx<T> b = mk<T>((c.y + m.y) * h, (m.x - c.x) * h);
+        cplx<T>* o = dst + (size_t)kz * plane + j;
+        if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(o) = make_float4(a.x, a.y, b.x, b.y);
+        else { o[0] = a; o[1] = b; }
+    };
+    if (warp == 0) {
+        // units 0 and R1/2 are their own partners
+        cplx<T> xa[R2];
+#pragma unroll
+        for (int g = 0; g < R2; ++g) xa[g] = E[(size_t)g * 32 + lane];
+        fft_radix<-1, R2>(xa);
+#pragma unroll
+        for (int c2 = 0; c2 < R2; ++c2) put(R1 * c2, xa[c2], xa[(R2 - c2) % R2]);
+#pragma unroll
+        for (int g = 0; g < R2; ++g) xa[g] = E[(size_t)((R1 / 2) * R2 + g) * 32 + lane];
+        fft_radix<-1, R2>(xa);
+#pragma unroll
+        for (int c2 = 0; c2 < R2; ++c2) put(R1 / 2 + R1 * c2, xa[c2], xa[R2 - 1 - c2]);
+    } else {
+        const int c1 = warp, c1m = R1 - warp;
+        cplx<T> xa[R2], xb[R2];
+#pragma unroll
+        for (int g = 0; g < R2; ++g) { xa[g] = E[(size_t)(c1 * R2 + g) * 32 + lane]; xb[g] = E[(size_t)(c1m * R2 + g) * 32 + lane]; }
+        fft_radix<-1, R2>(xa);
+        fft_radix<-1, R2>(xb);
+#pragma unroll
+        for (int c2 = 0; c2 < R2; ++c2) {
+            put(c1 + R1 * c2, xa[c2], xb[R2 - 1 - c2]);             // -kz = (R1 - c1) + R1 (R2 - 1 - c2)
+            put(c1m + R1 * c2, xb[c2], xa[R2 - 1 - c2]);
+        }
+    }
+}
+
+template <typename T, int Z>
+int rfft_z_half_launch(const void* src, void* dst, long long plane, int in_shift, const void* tw, cudaStream_t s) {
+    constexpr size_t smem = sizeof(cplx<T>) * ((size_t)Z + (size_t)Z * 32);
+    auto kern = rfft_z_half_kernel<T, Z>;
+    static thread_local bool configured[PYOTF_MAX_DEVICES] = {};
+    const int dev_slot = current_device_slot();
+    if (!configured[dev_slot]) {
+        PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev_slot] = true;
+    }
+    kern<<<(unsigned)(plane / 64), 16 * RegPlan<Z>::R1, smem, s>>>((const T*)src, (cplx<T>*)dst, plane, in_shift, (const cplx<T>*)tw);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T> int fft_twiddles(int L, const void** out, cudaStream_t s);
+template <int DIR, typename TIN, typename T>
+int fft_axis_launch(const AxisPass& p, const void* src, void* dst, int smem_limit, cudaStream_t s);
+
+// fftshift(fftn(ifftshift(x))) of a real [Z][Y][X] array using the Hermitian symmetry of its spectrum: the z pass
+// produces the planes kz = 0 .. Z/2 only (half-size scratch), the y pass runs in place on those, and the x pass writes
+// every line twice -- to its fftshift-ed position and, conjugated and reversed, to its Hermitian partner.  HBM / L2
+// traffic: 1 + 1 + 1 + 1 + 1 + 2 half-volumes (complex) instead of 0.5 + 2 + 2 + 2 + 2 + 2.
+template <typename T>
+int rfft3_shifted_run(const void* in, void* out, long long Z, long long Y, long long X, int smem_limit, cudaStream_t s, bool* done) {
+    *done = false;
+    static const bool off = getenv("PYOTF_B200_NO_RFFT3") != nullptr;      // A/B knob: the generic three full passes
+    if (off || !(Z == 64 || Z == 128 || Z == 256) || !(Y == 64 || Y == 128 || Y == 256 || Y == 512 || Y == 1024) ||
+        X % 32 != 0 || !is_pow2((int)X) || X < 64 || X > 1024 || (Y * X) % 64 != 0)
+        return 0;
+    if (fft_lines_reg_smem<T, 256>() > (size_t)smem_limit && Y >= 256) return 0;
+    const long long plane = Y * X, hz = Z / 2 + 1;
+    cplx<T>* W = nullptr;
+    keep_scratch_pool();
+    PYOTF_CUDA_OK(cudaMallocAsync(&W, sizeof(cplx<T>) * (size_t)hz * plane, s));
+    const void *twz = nullptr, *twy = nullptr, *twx = nullptr;
+    int rc = fft_twiddles<T>((int)Z, &twz, s);
+    if (!rc) rc = fft_twiddles<T>((int)Y, &twy, s);
+    if (!rc) rc = fft_twiddles<T>((int)X, &twx, s);
+    if (!rc) {
+        const int zshift = (int)((Z - Z / 2) % Z);
+        if (Z == 64) rc = rfft_z_half_launch<T, 64>(in, W, plane, zshift, twz, s);
+        else if (Z == 128) rc = rfft_z_half_launch<T, 128>(in, W, plane, zshift, twz, s);
+        else rc = rfft_z_half_launch<T, 256>(in, W, plane, zshift, twz, s);
+    }
+    if (!rc) {
+        AxisPass p;
+        p.L = (int)Y; p.n_outer = hz; p.n_inner = X;
+        p.in_shift = (int)((Y - Y / 2) % Y); p.out_shift = (int)(Y / 2); p.scale = 1.0; p.tw = twy; p.line_flags = nullptr;
+        rc = fft_axis_launch<-1, cplx<T>, T>(p, W, W, smem_limit, s);
+    }
+    if (!rc) {
+        AxisPass p;
+        p.L = (int)X; p.n_outer = hz * Y; p.n_inner = 1;
+        p.in_shift = (int)((X - X / 2) % X); p.out_shift = (int)(X / 2); p.scale = 1.0; p.tw = twx; p.line_flags = nullptr;
+        p.herm_Z = (int)Z; p.herm_Y = (int)Y;
+        rc = fft_axis_launch<-1, cplx<T>, T>(p, W, out, smem_limit, s);
+    }
+    cudaFreeAsync(W, s);
+    if (!rc) *done = true;
+    return rc;
+}
+
 // out = [shift](fftn / ifftn)([shift] in) over `axes` of a C-contiguous array.
 // pass_flags: optional, one pointer per pass in execution order (the LAST listed axis runs first): per-line
 // "has data" bytes, see AxisPass::line_flags.
@@ -158,6 +295,11 @@ int fftn_run(const void* in, void* out, int ndim, const long long* shape, const 
     int dev = 0, smem_limit = 0;
     PYOTF_CUDA_OK(cudaGetDevice(&dev));
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (real_in && !inverse && ndim == 3 && naxes == 3 && shift_in && shift_out && !pass_flags) {
+        bool done = false;
+        int rc = rfft3_shifted_run<T>(in, out, shape[0], shape[1], shape[2], smem_limit, s, &done);
+        if (rc || done) return rc;
+    }
     bool first = true;
     // contiguous axis last-to-first keeps the real->complex pass on the fastest axis when present
     for (int k = naxes - 1; k >= 0; --k) {

@@ -75,12 +75,10 @@ template <typename T> struct BigSymArgs {
     int K, H;
 };
 
-// first stage of an even 1024-point inverse transform for residue g, one transform per lane: ld(f) returns the
-// sample of frequency |f| (0 <= f <= H < 256); dst = E + lane receives Z_g[c1] and, for 0 < g < 16,
-// Z_{32-g}[c1] (c1 = 0 .. 16) at [(c1 * 32 + g) * LANES].
-template <typename T, int LANES, class LD>
-__device__ __forceinline__ void bigsym_stage1(LD ld, int H, int g, const cplx<T>* __restrict__ tws, cplx<T>* __restrict__ dst) {
-    cplx<T> x[32];
+// first stage of an even 1024-point inverse transform for residue g, one transform per lane.
+// bigsym_load: x[q] = sample of frequency 32 q + g (q < 8) / 32 q + g - 1024 (q >= 24) through ld(|f|), 0 <= |f| <= H < 256.
+// bigsym_stage1: dst = E + lane receives Z_g[c1] and, for 0 < g < 16, Z_{32-g}[c1] (c1 = 0 .. 16) at [(c1 * 32 + g) * LANES].
+template <typename T, class LD> __device__ __forceinline__ void bigsym_load(LD ld, int H, int g, cplx<T>* x) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int f = 32 * q + g;                       // frequency 32 q + g
@@ -91,6 +89,9 @@ __device__ __forceinline__ void bigsym_stage1(LD ld, int H, int g, const cplx<T>
         const int f = 1024 - 32 * q - g;                // frequency 32 q + g - 1024 = -f
         x[q] = f <= H ? ld(f) : mk<T>(0, 0);
     }
+}
+template <typename T, int LANES>
+__device__ __forceinline__ void bigsym_stage1(cplx<T>* x, int g, const cplx<T>* __restrict__ tws, cplx<T>* __restrict__ dst) {
     fft32_mid0<1>(x);
     dst[(size_t)g * LANES] = x[0];
     const bool mir = g > 0 && g < 16;
@@ -100,6 +101,33 @@ __device__ __forceinline__ void bigsym_stage1(LD ld, int H, int g, const cplx<T>
         const cplx<T> w = tws[g * c];
         dst[(size_t)(c * 32 + g) * LANES] = cmul(x[c], w);
         if (mir) dst[(size_t)(c * 32 + 32 - g) * LANES] = cmulc(x[32 - c], w);
+    }
+}
+
+// pupil-plane samples of one column for the first-stage loads: every load is issued before the first use
+// (kz * z -> e^{2 pi i kz z} -> * apodisation; the branch on the apodisation comes after all loads)
+template <typename T, bool EVEN, class PF>
+__device__ __forceinline__ void pupil_column_load(const double* __restrict__ kzc, PF pf, int K, int H, int g, bool col, double z, cplx<T>* x) {
+    double kz[16];
+    cplx<T> pv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int q = i < 8 ? i : i + 16;
+        const int fs = i < 8 ? 32 * q + g : 32 * q + g - 1024;        // signed frequency
+        const int f = EVEN && fs < 0 ? -fs : fs;
+        const bool ok = col && (fs >= 0 ? fs <= H : -fs <= H);
+        kz[i] = ok ? kzc[(ptrdiff_t)f * K] : 0.0;
+        pv[i] = ok ? pf((ptrdiff_t)f * K) : mk<T>(0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int q = i < 8 ? i : i + 16;
+        cplx<T> d = mk<T>(0, 0);
+        if (pv[i].x != (T)0 || pv[i].y != (T)0) {
+            cis_cycles(kz[i] * z, d);                                   // _calc_defocus   otf.py:357-360
+            d = cmul(d, pv[i]);
+        }
+        x[q] = d;
     }
 }
 
@@ -119,27 +147,17 @@ __global__ void __launch_bounds__(BigSymCfg<T>::NT, sizeof(T) == 4 ? 2 : 1) hans
     const int plane = blockIdx.y, kx0 = blockIdx.x * LANES, kx = kx0 + l16;
     const bool col = kx < NC;
     const double z = a.z[plane];
-    for (int k = tid; k < C::NTW; k += NT) tws[k] = a.tw[k];
-    __syncthreads();
+    cplx<T> x[32];
     if (active) {
         const T scale = (T)1.0 / ((T)C::N * (T)C::N);
-        const double* __restrict__ kzc = a.kzc + (size_t)H * K + H + kx;
         const T* __restrict__ amp = a.ampc + (size_t)H * K + H + kx;
-        auto ld = [&](int f) {
-            cplx<T> d = mk<T>(0, 0);
-            if (col) {
-                const T am = amp[(size_t)f * K];
-                if (am != (T)0) {
-                    cis_cycles(kzc[(size_t)f * K] * z, d);          // _calc_defocus   otf.py:357-360
-                    d = cscale(d, am * scale);
-                }
-            }
-            return d;
-        };
-        bigsym_stage1<T, LANES>(ld, H, unit, tws, E + l16);
+        auto pf = [&](ptrdiff_t o) { return mk<T>(amp[o] * scale, (T)0); };
+        pupil_column_load<T, true>(a.kzc + (size_t)H * K + H + kx, pf, K, H, unit, col, z, x);
     }
+    for (int k = tid; k < C::NTW; k += NT) tws[k] = a.tw[k];
     __syncthreads();
-    cplx<T> x[32];
+    if (active) bigsym_stage1<T, LANES>(x, unit, tws, E + l16);
+    __syncthreads();
     if (active) {
 #pragma unroll
         for (int g = 0; g < 32; ++g) x[g] = E[(size_t)(unit * 32 + g) * LANES + l16];
@@ -187,18 +205,19 @@ __global__ void __launch_bounds__(BigSymCfg<T>::NT, sizeof(T) == 4 ? 2 : 1) hans
     const int H = a.H, NC = H + 1;
     const int plane = blockIdx.y, y0 = blockIdx.x * LANES, y = y0 + l16;
     T* const psfi = a.psfi + (size_t)plane * N * N;
-    for (int k = tid; k < C::NTW; k += NT) tws[k] = a.tw[k];
-    __syncthreads();
     pdl_wait();                                                    // U comes from pass A
     const cplx<T>* __restrict__ Up = a.U + (size_t)plane * NC * C::UPITCH;
+    cplx<T> x[32];
     if (active) {
         const cplx<T>* __restrict__ u = Up + y;
         auto ld = [&](int f) { return u[(size_t)f * C::UPITCH]; };
-        bigsym_stage1<T, LANES>(ld, H, unit, tws, E + l16);
+        bigsym_load<T>(ld, H, unit, x);
     }
+    for (int k = tid; k < C::NTW; k += NT) tws[k] = a.tw[k];
+    __syncthreads();
+    if (active) bigsym_stage1<T, LANES>(x, unit, tws, E + l16);
     __syncthreads();
     if (active) {
-        cplx<T> x[32];
 #pragma unroll
         for (int g = 0; g < 32; ++g) x[g] = E[(size_t)(unit * 32 + g) * LANES + l16];
         fft32<1>(x);
@@ -287,10 +306,12 @@ template <typename T> struct BigGenCfg {
     static constexpr int NT = 256;                           // 32 quarter-warps = the 32 unit indices of a stage
     static constexpr int EPC = 16 / (int)sizeof(T);
     static constexpr int OQ = N / EPC + 1;                   // staging: x = EPC * m + j lives at [j][m]
-    static constexpr int OP = EPC * OQ + 1;                  // odd row pitch (reals)
+    static constexpr int OP = EPC * OQ;                      // row pitch (reals): rows land 4 banks (16 bytes) apart
     static constexpr int SP = N + 1;                         // odd pitch of the pass-A transpose tile [kx][y]
+    static constexpr int EC = R + 1;                         // exchange E[c1][EC][LANES]: units 4 w .. 4 w + 3 of a warp read disjoint banks
     static constexpr size_t tw_bytes() { return sizeof(cplx<T>) * (size_t)N; }
-    static constexpr size_t e_bytes() { return sizeof(cplx<T>) * (size_t)LANES * SP; }      // >= N * LANES: exchange, then transpose tile
+    static constexpr size_t e_bytes() { return sizeof(cplx<T>) * (size_t)R * EC * LANES; }   // >= LANES * SP: exchange, then transpose tile
+    static_assert((size_t)R * EC * LANES >= (size_t)LANES * SP, "transpose tile must fit the exchange");
     static constexpr size_t o_bytes() { return sizeof(T) * (size_t)LANES * OP + 16; }
     static constexpr size_t smem_a() { return tw_bytes() + e_bytes(); }
     static constexpr size_t smem_b() { return tw_bytes() + e_bytes() + o_bytes(); }
@@ -307,10 +328,9 @@ template <typename T> struct BigGenArgs {
     int K, H, accumulate;
 };
 
-// first stage of a band-limited (|f| <= H < 256) 1024-point inverse transform for residue g: ld(f), f signed
-template <typename T, int LANES, class LD>
-__device__ __forceinline__ void biggen_stage1(LD ld, int H, int g, const cplx<T>* __restrict__ tws, cplx<T>* __restrict__ dst) {
-    cplx<T> x[32];
+// first stage of a band-limited (|f| <= H < 256) 1024-point inverse transform for residue g
+// biggen_load: x[q] = sample of the signed frequency 32 q + g (q < 8) / 32 q + g - 1024 (q >= 24) through ld(f)
+template <typename T, class LD> __device__ __forceinline__ void biggen_load(LD ld, int H, int g, cplx<T>* x) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int f = 32 * q + g;
@@ -321,10 +341,13 @@ __device__ __forceinline__ void biggen_stage1(LD ld, int H, int g, const cplx<T>
         const int f = 32 * q + g - 1024;
         x[q] = f >= -H ? ld(f) : mk<T>(0, 0);
     }
+}
+template <typename T, int LANES, int EC>
+__device__ __forceinline__ void biggen_stage1(cplx<T>* x, int g, const cplx<T>* __restrict__ tws, cplx<T>* __restrict__ dst) {
     fft32_mid0<1>(x);
     dst[(size_t)g * LANES] = x[0];
 #pragma unroll
-    for (int c = 1; c < 32; ++c) dst[(size_t)(c * 32 + g) * LANES] = cmul(x[c], tws[(g * c) & 1023]);
+    for (int c = 1; c < 32; ++c) dst[(size_t)(c * EC + g) * LANES] = cmul(x[c], tws[(g * c) & 1023]);
 }
 
 template <typename T>
@@ -340,32 +363,25 @@ __global__ void __launch_bounds__(BigGenCfg<T>::NT, sizeof(T) == 4 ? 2 : 1) hans
     const int plane = blockIdx.y, ix0 = blockIdx.x * LANES, ix = ix0 + l8;
     const bool col = ix < K;
     const double z = a.z[plane];
-    for (int k = tid; k < C::N; k += NT) tws[k] = a.tw[k];
-    __syncthreads();
+    cplx<T> x[32];
     {
         const T scale = (T)1.0 / ((T)C::N * (T)C::N);
-        const double* __restrict__ kzc = a.kzc + (size_t)H * K + ix;
         const T* __restrict__ amp = a.ampc + (size_t)H * K + ix;
-        const cplx<T>* __restrict__ pup = a.pupilc ? a.pupilc + (size_t)H * K + ix : nullptr;
-        auto ld = [&](int f) {
-            cplx<T> d = mk<T>(0, 0);
-            if (col) {
-                const ptrdiff_t o = (ptrdiff_t)f * K;
-                const T am = amp[o];
-                if (am != (T)0 || pup) {
-                    cis_cycles(kzc[o] * z, d);                      // _calc_defocus   otf.py:357-360
-                    d = cscale(d, am * scale);
-                    if (pup) d = cmul(d, pup[o]);
-                }
-            }
-            return d;
-        };
-        biggen_stage1<T, LANES>(ld, H, unit, tws, E + l8);
+        if (a.pupilc) {
+            const cplx<T>* __restrict__ pup = a.pupilc + (size_t)H * K + ix;
+            auto pf = [&](ptrdiff_t o) { return cscale(pup[o], amp[o] * scale); };
+            pupil_column_load<T, false>(a.kzc + (size_t)H * K + ix, pf, K, H, unit, col, z, x);
+        } else {
+            auto pf = [&](ptrdiff_t o) { return mk<T>(amp[o] * scale, (T)0); };
+            pupil_column_load<T, false>(a.kzc + (size_t)H * K + ix, pf, K, H, unit, col, z, x);
+        }
     }
+    for (int k = tid; k < C::N; k += NT) tws[k] = a.tw[k];
     __syncthreads();
-    cplx<T> x[32];
+    biggen_stage1<T, LANES, C::EC>(x, unit, tws, E + l8);
+    __syncthreads();
 #pragma unroll
-    for (int g = 0; g < 32; ++g) x[g] = E[(size_t)(unit * 32 + g) * LANES + l8];
+    for (int g = 0; g < 32; ++g) x[g] = E[(size_t)(unit * C::EC + g) * LANES + l8];
     fft32<1>(x);
     __syncthreads();                                               // the exchange becomes the transpose tile S[kx][y]
     cplx<T>* const S = E;
@@ -397,19 +413,20 @@ __global__ void __launch_bounds__(BigGenCfg<T>::NT, sizeof(T) == 4 ? 2 : 1) hans
     const int H = a.H, K = a.K;
     const int plane = blockIdx.y, y0 = blockIdx.x * LANES, y = y0 + l8;
     T* const psfi = a.psfi + (size_t)plane * N * N;
-    for (int k = tid; k < N; k += NT) tws[k] = a.tw[k];
-    __syncthreads();
     pdl_wait();                                                    // W comes from pass A
+    cplx<T> x[32];
     {
         const cplx<T>* __restrict__ w = a.W + ((size_t)plane * K + H) * N + y;
         auto ld = [&](int f) { return w[(ptrdiff_t)f * N]; };
-        biggen_stage1<T, LANES>(ld, H, unit, tws, E + l8);
+        biggen_load<T>(ld, H, unit, x);
     }
+    for (int k = tid; k < N; k += NT) tws[k] = a.tw[k];
+    __syncthreads();
+    biggen_stage1<T, LANES, C::EC>(x, unit, tws, E + l8);
     __syncthreads();
     {
-        cplx<T> x[32];
 #pragma unroll
-        for (int g = 0; g < 32; ++g) x[g] = E[(size_t)(unit * 32 + g) * LANES + l8];
+        for (int g = 0; g < 32; ++g) x[g] = E[(size_t)(unit * C::EC + g) * LANES + l8];
         fft32<1>(x);
         T* const o = O + (size_t)l8 * OP + (unit % EPC) * OQ + unit / EPC;       // x = unit + 32 c2 staged as [x % EPC][x / EPC]
 #pragma unroll

@@ -63,6 +63,16 @@ def main():
             _, psfi = pup.handle(big).psf(zc, pup.tensor)
         torch.cuda.synchronize()
         print("big ok", float(psfi.sum()))
+    if "bigsym" in what:
+        from pyotf_b200.otf import HanserPSF
+
+        big = HanserPSF(wl=520, na=0.85, ni=1.0, res=130, zres=300, size=1024, zsize=1024, precision=precision)
+        hs, _ = big._handle_and_pupil(None)
+        zc = eng.to_device_f64(big.zrange[:26])
+        for _ in range(2):
+            _, psfi = hs.psf(zc, None)
+        torch.cuda.synchronize()
+        print("bigsym ok", float(psfi.sum()))
     if "otf" in what:
         from pyotf_b200.otf import HanserPSF
 
