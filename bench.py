@@ -228,7 +228,7 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100, extras=True):
            "scaling": "strong", "dtype": "f32" if precision == "fp32" else "f64",
            "workload": "retrieve_phase on the 25 x 256^2 fixture stack, 100 iterations, tol 0 (BASELINE config 2)",
            "rows_per_cta": st.rows_per_cta, "ctas_per_iteration": st.nparts,
-           "kernels_per_iteration": 2 if world == 1 else 3, "final_mse": float(mse[-1]),
+           "kernels_per_iteration": st.kernels_per_iteration(world > 1), "final_mse": float(mse[-1]),
            "parallelism": f"z-shard x{world}" + ("" if world == 1 else " + per-iteration sum over ranks inside the finalize "
                                                                       "kernel (peer windows over NVLink, no NCCL call)")}
     # roofline of one iteration: nz*N^2*s_r of measured data + 2 compact... full-grid pupils (in/out)
@@ -237,7 +237,8 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100, extras=True):
     peak, peak_src = measured_peaks()
     out["roofline"] = {"bound": "hbm", "achieved": alg / (best * 1e-3 / iters) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": alg / (best * 1e-3 / iters) / 1e9 / peak, "algorithmic_bytes_per_iteration": alg,
-                       "kernel": "pr_plane_kernel + pr_finalize_kernel", "peak_source": peak_src,
+                       "kernel": "pr_plane_kernel (fused finalize)" if st.kernels_per_iteration(world > 1) == 1 else "pr_plane_kernel + pr_finalize_kernel",
+                       "peak_source": peak_src,
                        "note": "the 7.6 MB working set of an iteration is L2-resident (ncu: 7.4 MB of DRAM reads per "
                                "plane-kernel launch only because ncu flushes caches), so HBM is not the binding limit: "
                                "the plane kernel is instruction-issue / latency bound on the 100 SMs its 100 CTAs occupy"}

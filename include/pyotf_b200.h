@@ -186,6 +186,11 @@ int pyotf_b200_pr_create(const pyotf_hanser_params* params, const double* z_dev,
 int pyotf_b200_pr_destroy(pyotf_pr_t* s);
 /* K, rows, f0 of the compact pupil layout; rows per CTA; partial pupils per iteration */
 int pyotf_b200_pr_info(const pyotf_pr_t* s, int* K, int* rows, int* f0, int* rows_per_cta, int* nparts);
+/* Kernel launches one iteration of pyotf_b200_pr_run takes on this state (loop body of phaseretrieval.py:95-130):
+ * 1 = the plane kernel finalizes the iteration itself behind a grid-wide arrival barrier (single GPU, every CTA
+ * resident); 2 = plane kernel + finalize kernel (long stacks; z-sharded runs with a peer window, where the finalize
+ * kernel also sums over the ranks); 3 = z-sharded with the NCCL fallback; 5 = the four-pass path of other sizes. */
+int pyotf_b200_pr_kernels_per_iteration(const pyotf_pr_t* s, int sharded, int* n);
 /* Inspection hook for the parity tests: device pointers of the intermediates of the last iteration
  * (four-pass path: W [nz][K][N] and P [nz][N][N] complex; both paths: partial pupils [nparts][K][K]). */
 int pyotf_b200_pr_debug_buffers(const pyotf_pr_t* s, void** W, void** P, void** partial);

@@ -170,6 +170,12 @@ class PRState:
         _lib.check(lib.pyotf_b200_pr_info(h, C.byref(K), C.byref(KR), C.byref(f0), C.byref(M), C.byref(nparts)))
         self.K, self.KR, self.f0, self.rows_per_cta, self.nparts = K.value, KR.value, f0.value, M.value, nparts.value
 
+    def kernels_per_iteration(self, sharded=False):
+        """Kernel launches per iteration of run() (1 = the plane kernel finalizes the iteration itself)."""
+        n = C.c_int()
+        _lib.check(_lib.load().pyotf_b200_pr_kernels_per_iteration(self._h, int(bool(sharded)), C.byref(n)))
+        return n.value
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "pyotf_b200_pr_create": (_i, [C.POINTER(HanserParams), _vp, _i, _ll, _vp, _i, _i, _vp, C.POINTER(_vp)]),
     "pyotf_b200_pr_destroy": (_i, [_vp]),
     "pyotf_b200_pr_info": (_i, [_vp, _ip, _ip, _ip, _ip, _ip]),
+    "pyotf_b200_pr_kernels_per_iteration": (_i, [_vp, _i, _ip]),
     "pyotf_b200_pr_debug_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "pyotf_b200_pr_set_pupil": (_i, [_vp, _vp, _vp]),
     "pyotf_b200_pr_get_pupil": (_i, [_vp, _i, _vp, _vp]),

@@ -433,7 +433,7 @@ int pyotf_b200_pr_destroy(pyotf_pr_t* s) {
         cudaFree(s->win);
     }
     void* bufs[] = {s->z, s->data, s->pupil[0], s->pupil[1], s->partial, s->mse_part, s->sums, s->diffpart, s->mse,
-                    s->mse_diff, s->pupil_diff, s->state, s->dtab, s->W, s->P};
+                    s->mse_diff, s->pupil_diff, s->state, s->dtab, s->W, s->P, s->arrive};
     for (void* b : bufs) if (b) cudaFreeAsync(b, st);         // stream-ordered: returns to the cached pool
     if (s->h_flags) { cudaFreeHost(s->h_flags); for (int i = 0; i < 4; ++i) cudaEventDestroy(s->ev[i]); }
     pyotf_b200_hanser_destroy(s->h);
@@ -448,6 +448,14 @@ int pyotf_b200_pr_info(const pyotf_pr_t* s, int* K, int* rows, int* f0, int* row
     if (f0) *f0 = s->h->f0;
     if (rows_per_cta) *rows_per_cta = s->M;
     if (nparts) *nparts = s->nparts;
+    return 0;
+}
+
+int pyotf_b200_pr_kernels_per_iteration(const pyotf_pr_t* s, int sharded, int* n) {
+    PYOTF_REQUIRE(s && n, "pr_kernels_per_iteration: null argument");
+    if (s->generic) *n = 5;
+    else if (sharded) *n = (s->win && s->win_world >= 1) ? 2 : 3;
+    else *n = (s->fuse && s->dtab) ? 1 : 2;
     return 0;
 }
 

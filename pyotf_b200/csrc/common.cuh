@@ -95,6 +95,8 @@ struct pyotf_pr {
     double *mse = nullptr, *mse_diff = nullptr, *pupil_diff = nullptr;   // [cap_iters]
     void* dtab = nullptr;           // [nz][dtab_size] defocus tables of this stack (built once)
     void* state = nullptr;          // PrState
+    unsigned* arrive = nullptr;     // grid-arrival counter of the fused (one kernel per iteration) loop
+    int fuse = 0;                   // the plane kernel finalizes the iteration itself (single GPU, <= 1 CTA per SM)
     cudaStream_t stream = nullptr;  // creation stream: the state's buffers are stream-ordered allocations on it
     // z-sharded runs: peer-mapped window (CUDA IPC; layout in pr.cuh) into which every rank's finalize kernel pushes
     // its partial sums over NVLink

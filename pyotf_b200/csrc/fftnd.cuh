@@ -23,7 +23,7 @@ struct AxisPass {
     const void* tw;        // [L] e^{+2 pi i k / L} in the transform's dtype (device; cached per length)
     const unsigned char* line_flags;   // optional: one byte per line (outer * n_inner + inner); 0 = the line is
                                        // entirely zero on input, so (in place) it is left untouched
-    int herm_Z = 0, herm_Y = 0;        // last pass of the real 3D transform (contiguous axis only): the source holds
+    int herm_Z = 0, herm_Y = 0, herm_Yshift = 0;   // last pass of the real 3D transform (contiguous axis only): the source holds
                                        // the planes kz = 0 .. Z/2 of [kz][y-shifted][x]; line (kz, ys) is stored to the
                                        // fftshift-ed plane (kz + Z/2) % Z and, for 0 < kz < Z/2, its complex conjugate
                                        // to the Hermitian partner ((-zs) % Z, (-ys) % Y, (-xs) % X)
@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
                 const int pos = digit_reversed_pos<L>(o);
                 const cplx<T> v = cscale(res[(size_t)t * pitch + fft_pad<POW2>(pos)], scale);
                 if (p.herm_Z) {
-                    const long long line = outer + t;
-                    const int kz = (int)(line / p.herm_Y), ys = (int)(line - (long long)kz * p.herm_Y), hz = p.herm_Z / 2;
+                    const int line = (int)outer + t;                    // herm_Y is a power of two
+                    const int kz = line >> p.herm_Yshift, ys = line & (p.herm_Y - 1), hz = p.herm_Z / 2;
                     const int zs = kz + hz == p.herm_Z ? 0 : kz + hz;
                     dst[((size_t)zs * p.herm_Y + ys) * L + l] = v;
                     if (kz > 0 && kz < hz) {
@@ -271,8 +271,8 @@ __global__ void __launch_bounds__(256) fft_axis_kernel(AxisPass p, const TIN* __
             if constexpr (POW2) pos = digit_reversed_pos<L>(o);
             const cplx<T> v = cscale(res[(size_t)t * pitch + fft_pad<POW2>(pos)], scale);
             if (p.herm_Z) {
-                const long long line = outer + t;
-                const int kz = (int)(line / p.herm_Y), ys = (int)(line - (long long)kz * p.herm_Y), hz = p.herm_Z / 2;
+                const int line = (int)outer + t;                        // herm_Y is a power of two
+                const int kz = line >> p.herm_Yshift, ys = line & (p.herm_Y - 1), hz = p.herm_Z / 2;
                 const int zs = kz + hz == p.herm_Z ? 0 : kz + hz;
                 dst[((size_t)zs * p.herm_Y + ys) * Lr + l] = v;
                 if (kz > 0 && kz < hz) {

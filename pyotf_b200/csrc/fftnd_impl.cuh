@@ -278,7 +278,8 @@ int rfft3_shifted_run(const void* in, void* out, long long Z, long long Y, long 
         AxisPass p;
         p.L = (int)X; p.n_outer = hz * Y; p.n_inner = 1;
         p.in_shift = (int)((X - X / 2) % X); p.out_shift = (int)(X / 2); p.scale = 1.0; p.tw = twx; p.line_flags = nullptr;
-        p.herm_Z = (int)Z; p.herm_Y = (int)Y;
+        p.herm_Z = (int)Z; p.herm_Y = (int)Y; p.herm_Yshift = 0;
+        while ((1 << p.herm_Yshift) < (int)Y) ++p.herm_Yshift;
         rc = fft_axis_launch<-1, cplx<T>, T>(p, W, out, smem_limit, s);
     }
     cudaFreeAsync(W, s);

@@ -21,11 +21,29 @@
 
 namespace pyotf {
 
+// Phase timestamps (debug builds only: -DPYOTF_PR_TIMING, tools/pr_phases.py): globaltimer marks per CTA
+#ifdef PYOTF_PR_TIMING
+static __device__ unsigned long long g_pr_marks[256 * 16];
+#define PR_MARK(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_pr_marks[blockIdx.x * 16 + (i)] = t_; } } while (0)
+#else
+#define PR_MARK(i) do { } while (0)
+#endif
+
 struct PrState {
     int stopped;        // set by the finalize kernel when a tolerance is met
     int iters_run;      // number of entries of mse / mse_diff / pupil_diff that are valid
     int final_is_next;  // 1: the loop ran out, the final pupil is one update past the last applied one
     int pad;
+};
+
+struct PrFinalArgs {
+    int iter, K, nparts;
+    int nmse;               // entries of mse_part (one per CTA of the kernel that compared model and data)
+    int cur;                // which pupil buffer holds the pupil this iteration applied
+    int phase_only, last_iter;
+    double npix_total;      // nz_total * N * N   (mean of the squared error)
+    double nz_total;        // planes over all ranks (mean over z of the new pupils)
+    double pupil_tol, mse_tol;
 };
 
 template <typename T> struct PrPlaneArgs {
@@ -40,6 +58,14 @@ template <typename T> struct PrPlaneArgs {
     const PrState* state;
     int K, KR, KP, f0, nz;
     int pdl;                    // launched with programmatic stream serialization (host-side flag only)
+    // fused finalize (FUSE variants: every CTA of the grid is resident; see pr_fused_finalize)
+    unsigned* arrive;           // grid-arrival counter, monotonic over the iterations of a run (zeroed by pr_run)
+    PrFinalArgs fin;
+    const unsigned char* mask;
+    cplx<T>* pupil0; cplx<T>* pupil1;
+    double* diffpart;           // [2][gridDim.x][2]
+    double *mse, *mse_diff, *pupil_diff;
+    PrState* state_rw;
 };
 
 // new_psf = sqrt(max(data, 0)) * exp(i angle(a))  (psqrt, phaseretrieval.py:79; :120-122), I = |a|^2.
@@ -67,13 +93,16 @@ __device__ __forceinline__ cplx<float> replace_magnitude(cplx<float> a, float I,
 
 // NTH = 256 (two CTAs per SM) or 512 (one wide CTA per SM: short stacks, where there are fewer plane
 // quarters than SMs and latency hiding has to come from inside the CTA).
-template <typename T, int N, int M, bool TAB, int NTH>
+template <typename T, int NT> __device__ void pr_fused_finalize(const PrPlaneArgs<T>& a, double* red);
+
+template <typename T, int N, int M, bool TAB, int NTH, bool FUSE = false>
 __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) pr_plane_kernel(PrPlaneArgs<T> a) {
     using RP = FftPlan<N>;
     using CP = FftPlan<M>;
     using SM = HanserSmem<N, M, T, NTH>;
     constexpr int NT = SM::NT;
     constexpr int R = N / M;
+    PR_MARK(0);
     pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[NT / 32];
@@ -110,6 +139,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
     // everything above reads per-stack constants only; the pupil, the state word and the partial-pupil
     // buffer belong to the previous finalize kernel until it has completed
     pdl_wait();
+    PR_MARK(1);
     if (a.state->stopped) return;
     __syncthreads();
     // ---------------- inverse: fold + columns ----------------
@@ -131,6 +161,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
         }
     }
     __syncthreads();
+    PR_MARK(2);
     // ---------------- rows: inverse FFT_N, magnitude replacement, forward FFT_N ----------------
     double mse_acc = 0.0;
     {
@@ -199,6 +230,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
         }
     }
     __syncthreads();
+    PR_MARK(3);
     // ---------------- forward columns: FFT_M over y' (transpose of the inverse stages) ----------------
     {
         constexpr int Q1 = CP::R1, L1 = CP::R2, JMAX = N / L1;
@@ -256,6 +288,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
             }
         }
     }
+    PR_MARK(4);
     // ---------------- block reduction of the squared error ----------------
     for (int o = 16; o; o >>= 1) mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
     if ((tid & 31) == 0) red[tid >> 5] = mse_acc;
@@ -265,6 +298,9 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
         for (int w = 0; w < NT / 32; ++w) s += red[w];
         a.mse_part[blockIdx.x] = s;
     }
+    PR_MARK(5);
+    if constexpr (FUSE) pr_fused_finalize<T, NT>(a, reinterpret_cast<double*>(smem_raw));
+    PR_MARK(9);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -330,16 +366,6 @@ struct PrPeers {
     void* win[PYOTF_MAX_PEERS];         // every rank's window as mapped into this process (fixed rank order)
 };
 
-struct PrFinalArgs {
-    int iter, K, nparts;
-    int nmse;               // entries of mse_part (one per CTA of the kernel that compared model and data)
-    int cur;                // which pupil buffer holds the pupil this iteration applied
-    int phase_only, last_iter;
-    double npix_total;      // nz_total * N * N   (mean of the squared error)
-    double nz_total;        // planes over all ranks (mean over z of the new pupils)
-    double pupil_tol, mse_tol;
-};
-
 // deterministic warp sum of v[0], v[stride], ... (n terms): same order in every CTA.  The loads of a
 // chunk of 16 x 32 terms are all issued before the first add, so a sum costs one L2 round trip.
 __device__ __forceinline__ double warp_sum_fixed(const double* __restrict__ v, int n, int stride, int lane) {
@@ -360,6 +386,155 @@ __device__ __forceinline__ double warp_sum_fixed(const double* __restrict__ v, i
 
 constexpr int PR_FIN_PIX = 32;      // pixels per finalize CTA
 constexpr int PR_FIN_LANES = 8;     // threads sharing one pixel's sum over the partials
+
+// pr_finalize_kernel inside the plane kernel (single GPU, every CTA of the grid resident -- the grid has at most one
+// CTA per SM): after a grid-wide arrival barrier CTA b reduces the partial pupils of ITS share of the pixels, in the
+// same summation order as pr_finalize_kernel (8 lanes per pixel, lane l adds the parts l, l + 8, ... in order, then the
+// lanes are added in order), so both paths produce bit-identical pupils.  The scalars (mse, mse_diff, pupil_diff, the
+// stop decision) are evaluated redundantly and identically by every CTA.  One kernel per iteration.
+template <typename T, int NT> __device__ void pr_fused_finalize(const PrPlaneArgs<T>& a, double* smem_d) {
+    const int tid = threadIdx.x, nblk = gridDim.x;
+    const PrFinalArgs& f = a.fin;
+    __shared__ int s_stop;
+    const double old_mse = (tid == 0 && f.iter > 0) ? a.mse[f.iter - 1] : 0.0;      // written by the previous launch
+    // ---- grid barrier: this CTA's partial pupil and squared-error sum are visible before it arrives -------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(a.arrive, 1u);
+        const unsigned target = (unsigned)(f.iter + 1) * (unsigned)nblk;
+        unsigned seen;
+        unsigned long long t0 = 0;
+        s_stop = 0;
+        for (unsigned spin = 0;; ++spin) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.arrive) : "memory");
+            if ((int)(seen - target) >= 0) break;
+            if ((spin & 1023u) == 1023u) {                      // bounded: a CTA of this grid never became resident
+                unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t0 == 0) t0 = t1;
+                else if (t1 - t0 > 2000000000ull) { s_stop = 2; a.state_rw->stopped = 3; break; }
+            }
+        }
+    }
+    __syncthreads();
+    PR_MARK(6);
+    if (s_stop == 2) return;
+    const int KK = f.K * f.K;
+    constexpr int PIX = NT / PR_FIN_LANES;                              // pixels per pass
+    const int per = (KK + nblk - 1) / nblk, p0 = blockIdx.x * per, p1 = min(KK, p0 + per);
+    const int px = tid % PIX, lane = tid / PIX;
+    double2* red2 = reinterpret_cast<double2*>(smem_d);                 // [PR_FIN_LANES][PIX]
+    double* redn = smem_d + 2 * NT;                                     // [NT / 32][2]
+    double* scal = redn + 2 * (NT / 32);                                // squared-error sum, pupil-difference numerator / denominator
+    // ---- every load of the first pass is issued before anything waits: the partial pupils of this CTA's pixels (all
+    //      threads) and the three scalar sums (warps 0 .. 2, one each) share one L2 round trip -----------------------
+    if (tid < 96) {
+        const int w = tid >> 5, l = tid & 31;
+        const double* src = w == 0 ? a.mse_part : a.diffpart + (size_t)(f.iter & 1) * 2 * nblk + (w - 1);
+        const int n = w == 0 ? f.nmse : nblk, stride = w == 0 ? 1 : 2;
+        double sv = 0.0;
+        if (w == 0 || f.iter > 0) sv = warp_sum_fixed(src, n, stride, l);
+        if (l == 0) scal[w] = sv;
+    }
+    constexpr int NPB = 16;                                             // parts per lane and batch
+    cplx<T> v[NPB];
+    {
+        const int p = p0 + px;
+        const bool live = p < p1 && a.mask[p];                          // pixels outside the pupil are zero whatever the sum
+        const cplx<T>* __restrict__ pp = a.partial + p;
+#pragma unroll
+        for (int k = 0; k < NPB; ++k) {
+            const int q = lane + k * PR_FIN_LANES;
+            v[k] = (live && q < f.nparts) ? pp[(size_t)q * KK] : mk<T>(0, 0);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double new_mse = scal[0] / f.npix_total;
+        double md = nan(""), pd = nan("");
+        if (f.iter > 0) {
+            md = fabs(old_mse - new_mse) / old_mse;                    // phaseretrieval.py:103
+            pd = scal[1] / scal[2];                                    // :105
+        }
+        const int stop = (pd < f.pupil_tol) || (md < f.mse_tol) || (new_mse < f.mse_tol);   // :114
+        s_stop = stop;
+        if (blockIdx.x == 0) {
+            a.mse[f.iter] = new_mse; a.mse_diff[f.iter] = md; a.pupil_diff[f.iter] = pd;
+            a.state_rw->iters_run = f.iter + 1;
+            if (stop) { a.state_rw->final_is_next = 0; a.state_rw->stopped = 1; }
+            else if (f.last_iter) a.state_rw->final_is_next = 1;
+        }
+    }
+    __syncthreads();
+    PR_MARK(7);
+    if (s_stop) return;
+    const cplx<T>* __restrict__ oldp = f.cur ? a.pupil1 : a.pupil0;
+    cplx<T>* __restrict__ newp = f.cur ? a.pupil0 : a.pupil1;
+    double num = 0.0, den = 0.0;
+    for (int base = p0; base < p1; base += PIX) {
+        const int p = base + px;
+        double sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int k = 0; k < NPB; ++k) { sx += (double)v[k].x; sy += (double)v[k].y; }
+        if (p < p1 && a.mask[p]) {
+            const cplx<T>* __restrict__ pp = a.partial + p;
+            for (int q0 = lane + NPB * PR_FIN_LANES; q0 < f.nparts; q0 += NPB * PR_FIN_LANES) {     // more than 128 parts
+                cplx<T> u[NPB];
+#pragma unroll
+                for (int k = 0; k < NPB; ++k) {
+                    const int q = q0 + k * PR_FIN_LANES;
+                    u[k] = q < f.nparts ? pp[(size_t)q * KK] : mk<T>(0, 0);
+                }
+#pragma unroll
+                for (int k = 0; k < NPB; ++k) { sx += (double)u[k].x; sy += (double)u[k].y; }
+            }
+        }
+        // the next pass's first batch is in flight while this one is reduced
+        {
+            const int pn = p + PIX;
+            const bool live = pn < p1 && a.mask[pn];
+            const cplx<T>* __restrict__ pp = a.partial + pn;
+#pragma unroll
+            for (int k = 0; k < NPB; ++k) {
+                const int q = lane + k * PR_FIN_LANES;
+                v[k] = (live && q < f.nparts) ? pp[(size_t)q * KK] : mk<T>(0, 0);
+            }
+        }
+        if (base != p0) __syncthreads();
+        red2[lane * PIX + px] = make_double2(sx, sy);
+        __syncthreads();
+        if (lane == 0 && p < p1) {
+            sx = 0.0; sy = 0.0;
+#pragma unroll
+            for (int l = 0; l < PR_FIN_LANES; ++l) { sx += red2[l * PIX + px].x; sy += red2[l * PIX + px].y; }
+            const double m = a.mask[p] ? 1.0 : 0.0;
+            sx = sx / f.nz_total * m; sy = sy / f.nz_total * m;        // mean(0) * mask   :127
+            if (f.phase_only) {                                        // exp(i angle(.)) * mask   :130
+                const double mag = hypot(sx, sy);
+                if (mag > 0.0) { sx = sx / mag * m; sy = sy / mag * m; }
+                else { sx = m; sy = 0.0; }
+            }
+            const cplx<T> o = oldp[p];
+            const cplx<T> nv = mk<T>((T)sx, (T)sy);
+            newp[p] = nv;
+            const double dx = (double)o.x - (double)nv.x, dy = (double)o.y - (double)nv.y;
+            num += dx * dx + dy * dy;
+            den += (double)o.x * (double)o.x + (double)o.y * (double)o.y;
+        }
+    }
+    PR_MARK(8);
+    // deterministic block sums of num / den (fixed shuffle tree, warps added in order)
+    for (int o = 16; o; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
+    __syncthreads();
+    if ((tid & 31) == 0) { redn[2 * (tid >> 5)] = num; redn[2 * (tid >> 5) + 1] = den; }
+    __syncthreads();
+    if (tid == 0) {
+        double n2 = 0.0, d2 = 0.0;
+        for (int w = 0; w < NT / 32; ++w) { n2 += redn[2 * w]; d2 += redn[2 * w + 1]; }
+        double* dp = a.diffpart + (size_t)((f.iter + 1) & 1) * 2 * nblk;
+        dp[2 * blockIdx.x] = n2; dp[2 * blockIdx.x + 1] = d2;
+    }
+}
 
 // TP = cplx<T> (per-CTA partials of this rank) or double2 (all-reduced sums: nparts = 1 and
 // the squared-error numerator sits at index KK).  Block = 256 threads = 32 pixels x 8 part lanes.

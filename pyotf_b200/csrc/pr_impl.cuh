@@ -46,10 +46,10 @@ template <typename T> int pr_pick_rows(const pyotf_hanser* h, int nz, int smem_l
     return pick;
 }
 
-template <typename T, int N, int M, bool TAB, int NTH>
+template <typename T, int N, int M, bool TAB, int NTH, bool FUSE = false>
 int pr_plane_launch_nmt(const PrPlaneArgs<T>& a, cudaStream_t s) {
     const size_t smem = HanserSmem<N, M, T, NTH>::bytes(a.KP);
-    auto kern = pr_plane_kernel<T, N, M, TAB, NTH>;
+    auto kern = pr_plane_kernel<T, N, M, TAB, NTH, FUSE>;
     static thread_local size_t configured[PYOTF_MAX_DEVICES] = {};      // the attribute is per device
     const int dev_slot = current_device_slot();
     if (smem > configured[dev_slot]) {
@@ -73,6 +73,10 @@ int pr_plane_launch_nmt(const PrPlaneArgs<T>& a, cudaStream_t s) {
 
 template <typename T, int N, int M>
 int pr_plane_launch_nm(const pyotf_hanser* h, int nth, const PrPlaneArgs<T>& a, cudaStream_t s) {
+    if constexpr (N == 256 && M == 64) {
+        // fused finalize (one kernel per iteration): the 256^2 table variants only
+        if (a.arrive && a.dtab) return nth == 512 ? pr_plane_launch_nmt<T, N, M, true, 512, true>(a, s) : pr_plane_launch_nmt<T, N, M, true, 256, true>(a, s);
+    }
     if (nth == 512) {
         // the wide variant needs at least 512 / 32 = 16 warps of column work: only the 256^2 plans
         if constexpr (N == 256 && M == 64)
@@ -89,10 +93,15 @@ template <typename T, int N> int pr_plane_launch_n(const pyotf_hanser* h, int M,
     return 1;
 }
 
-template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, bool pdl, cudaStream_t st) {
+template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, bool pdl, cudaStream_t st, const PrFinalArgs* fin = nullptr) {
     const pyotf_hanser* h = s->h;
     PrPlaneArgs<T> a;
     a.pdl = pdl ? 1 : 0;
+    a.arrive = nullptr;
+    if (fin) {
+        a.arrive = s->arrive; a.fin = *fin; a.mask = h->maskc; a.pupil0 = (cplx<T>*)s->pupil[0]; a.pupil1 = (cplx<T>*)s->pupil[1];
+        a.diffpart = s->diffpart; a.mse = s->mse; a.mse_diff = s->mse_diff; a.pupil_diff = s->pupil_diff; a.state_rw = (PrState*)s->state;
+    }
     a.kzc = h->kzc; a.pupilc = (const cplx<T>*)s->pupil[cur]; a.tw = (const cplx<T>*)h->tw; a.dtab = (const cplx<T>*)s->dtab; a.z = s->z;
     a.data = (const T*)s->data; a.partial = (cplx<T>*)s->partial; a.mse_part = s->mse_part; a.state = (const PrState*)s->state;
     a.K = h->K; a.KR = h->KR; a.KP = h->KP; a.f0 = h->f0; a.nz = s->nz;
@@ -150,6 +159,12 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
     PYOTF_CUDA_OK(cudaMallocAsync(&s->diffpart, (size_t)4 * s->nblk * sizeof(double), st));
     PYOTF_CUDA_OK(cudaMallocAsync(&s->state, sizeof(PrState), st));
     PYOTF_CUDA_OK(cudaMemsetAsync(s->state, 0, sizeof(PrState), st));
+    PYOTF_CUDA_OK(cudaMallocAsync(&s->arrive, sizeof(unsigned), st));
+    PYOTF_CUDA_OK(cudaMemsetAsync(s->arrive, 0, sizeof(unsigned), st));
+    // one kernel per iteration when every CTA of the plane kernel is resident at once (a grid-wide arrival barrier
+    // inside the kernel replaces the finalize launch): 256^2, 64 rows per CTA, at most one CTA per SM
+    const bool no_fuse = getenv("PYOTF_B200_PR_NO_FUSE") != nullptr;     // read at every create: tests compare the two loops
+    s->fuse = (!no_fuse && !s->generic && h->N == 256 && s->M == 64 && s->nparts <= sms && 2 * s->nparts >= sms) ? 1 : 0;
     const unsigned nb = (unsigned)((npix + 255) / 256);
     if (data_dtype == PYOTF_F32) pr_convert_data_kernel<float, T><<<nb, 256, 0, st>>>((const float*)data, (T*)s->data, npix);
     else pr_convert_data_kernel<double, T><<<nb, 256, 0, st>>>((const double*)data, (T*)s->data, npix);
@@ -222,6 +237,8 @@ template <typename T> int pr_generic_passes(pyotf_pr* s, int cur, cudaStream_t s
 
 int comm_allreduce_f64(pyotf_comm* c, double* buf, long long n, cudaStream_t st);
 
+inline bool dbg_skip_any() { static const bool v = getenv("PYOTF_B200_PR_DEBUG_SKIP") != nullptr; return v; }
+
 template <class K, class... A>
 int pr_launch(bool pdl, K kern, dim3 grid, dim3 block, cudaStream_t st, A... args) {
     cudaLaunchConfig_t cfg = {};
@@ -265,6 +282,8 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
     // over NVLink and the loop keeps its programmatic launches; without one it falls back to an NCCL all-reduce
     const bool window = comm && s->win && s->win_world >= 1;
     const bool use_pdl = (!comm || window) && !s->generic && !no_pdl;
+    const bool fused = s->fuse && !comm && s->dtab && !dbg_skip_any();
+    if (fused) PYOTF_CUDA_OK(cudaMemsetAsync(s->arrive, 0, sizeof(unsigned), st));
     PrPeers peers = {};
     if (window) { peers.world = s->win_world; peers.rank = s->win_rank; for (int r = 0; r < s->win_world; ++r) peers.win[r] = s->peer[r]; }
     for (int i = 0; i < max_iters; ++i) {
@@ -274,9 +293,25 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
             if (s->h_flags[slot]) break;
         }
         const int cur = (start + i) & 1;
-        int rc = s->generic ? pr_generic_passes<T>(s, cur, st) : pr_plane_launch<T>(s, cur, use_pdl, st);
-        if (rc) return rc;
+        static const int dbg_skip = [] { const char* e = getenv("PYOTF_B200_PR_DEBUG_SKIP"); return e ? atoi(e) : 0; }();   // timing experiments only: 1 = no plane kernel, 2 = no finalize
+        int rc = 0;
         fa.iter = i; fa.cur = cur; fa.last_iter = i == max_iters - 1; fa.nmse = s->nmse;
+        if (fused) {
+            fa.nparts = s->nparts;
+            rc = pr_plane_launch<T>(s, cur, use_pdl, st, &fa);
+            if (rc) return rc;
+            ++launched;
+            if (i % CHK == CHK - 1) {
+                const int slot = (i / CHK) % NSLOT;
+                PYOTF_CUDA_OK(cudaMemcpyAsync(&s->h_flags[slot], &((PrState*)s->state)->stopped, sizeof(int), cudaMemcpyDeviceToHost, st));
+                PYOTF_CUDA_OK(cudaEventRecord(s->ev[slot], st));
+            }
+            continue;
+        }
+        if (dbg_skip != 1) rc = s->generic ? pr_generic_passes<T>(s, cur, st) : pr_plane_launch<T>(s, cur, use_pdl, st);
+        if (rc) return rc;
+        fa.nmse = s->nmse;                              // the generic pass B sets it at every launch
+        if (dbg_skip == 2) { ++launched; continue; }
         if (window) {
             peers.slot = i & 1; peers.epoch = s->epoch_base + i + 1;
             fa.nparts = s->nparts;
@@ -329,6 +364,7 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
     const int n = hs.iters_run;
     if (window) s->epoch_base += max_iters;            // the same on every rank, whatever was enqueued after a stop
     PYOTF_REQUIRE(hs.stopped != 2, "pr_run: a peer rank did not publish its partial sums in time (z-sharded run)");
+    PYOTF_REQUIRE(hs.stopped != 3, "pr_run: the grid-wide barrier of the fused iteration timed out (plane-kernel CTAs not co-resident)");
     PYOTF_REQUIRE(n >= 1 && n <= launched, "pr_run: inconsistent device state");
     s->applied = (start + n - 1) & 1;                  // the pupil iteration n-1 applied   (result.model)
     s->cur = hs.stopped ? s->applied : (s->applied ^ 1);   // final new_pupil                  :144-148

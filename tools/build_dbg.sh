@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p tools/_dbg
-F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -DPYOTF_K1_TIMING"
+F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -DPYOTF_K1_TIMING -DPYOTF_PR_TIMING"
 for src in ${@:-hanser_sym_f32}; do
   nvcc $F -c pyotf_b200/csrc/$src.cu -o tools/_dbg/$src.o &
 done
