@@ -7,6 +7,7 @@
 //   pass 3 (z): transform + 1/n scaling + |.|^2 accumulated over the polarisation components into PSFi
 //           (and / or the PSFa store), so neither OTFa nor a separate |.|^2 pass touches HBM.
 #pragma once
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -26,6 +27,7 @@ template <typename T> struct ShepArgs {
     const cplx<T>* tw_x;        // [N]
     const cplx<T>* tw_z;        // [NZ]
     const unsigned char* planeflag;   // [NZ][N]: 1 where the (memory-layout) plane zm can hold shell voxels
+    int band0[2], bandn[2];           // the same planes as up to two runs [band0, band0 + bandn) of zm (bandn[0] < 0: use planeflag)
     int accumulate;
     double scale;
 };
@@ -134,7 +136,12 @@ template <typename T> struct ShepCol : NoAcc {
     }
     __device__ __forceinline__ cplx<T> load(const Line& d, int l) const {
         int zm = l + a.in_z; if (zm >= a.p.NZ) zm -= a.p.NZ;
-        if (!a.planeflag[(size_t)zm * a.p.N]) return mk<T>(0, 0);     // never written: the plane holds no shell voxel
+        // planes that hold no shell voxel were never written
+        if (a.bandn[0] >= 0) {
+            if ((unsigned)(zm - a.band0[0]) >= (unsigned)a.bandn[0] && (unsigned)(zm - a.band0[1]) >= (unsigned)a.bandn[1]) return mk<T>(0, 0);
+        } else if (!a.planeflag[(size_t)zm * a.p.N]) {
+            return mk<T>(0, 0);
+        }
         return d.in[(size_t)zm * a.p.N * a.p.N];
     }
     __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v, int&) const {
@@ -168,6 +175,23 @@ int sheppard_fused(const SheppardParams& p, void* psfa_out, void* psfi_out, cuda
     PYOTF_CUDA_OK(cudaGetLastError());
     ShepArgs<T> a;
     a.p = p; a.tmp = tmp; a.planeflag = planeflag;
+    {
+        // the predicate of sheppard_planeflag_kernel on the host: the occupied planes as runs of the memory index zm
+        a.band0[0] = a.band0[1] = 0; a.bandn[0] = a.bandn[1] = 0;
+        int runs = 0;
+        bool prev = false;
+        const double dmax = std::fmax(std::fabs(p.dk), std::fabs(p.dkz));
+        for (int zm = 0; zm < p.NZ; ++zm) {
+            int zu = zm - p.NZ / 2; if (zu < 0) zu += p.NZ;
+            const int f = zu < (p.NZ + 1) / 2 ? zu : zu - p.NZ;
+            const double kz = (double)f * p.kzstep, kzz = p.dual ? std::fabs(kz) : kz;
+            const bool on = kzz > p.kz_min && std::fabs(kz) <= (p.kmag + dmax) * (1.0 + 1e-9);
+            if (on && !prev) { if (runs < 2) a.band0[runs] = zm; ++runs; }
+            if (on && runs <= 2) ++a.bandn[runs - 1];
+            prev = on;
+        }
+        if (runs > 2) a.bandn[0] = -1;
+    }
     const void *twx = nullptr, *twz = nullptr;
     int rc = sizeof(T) == 4 ? fft_twiddles_f32(p.N, &twx, s) : fft_twiddles_f64(p.N, &twx, s);
     if (!rc) rc = sizeof(T) == 4 ? fft_twiddles_f32(p.NZ, &twz, s) : fft_twiddles_f64(p.NZ, &twz, s);

@@ -319,8 +319,8 @@ def test_phase_retrieval_object_keeps_state_step_and_set_pupil():
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp64"])
-@pytest.mark.parametrize("nz,phase_only,ptol", [(25, False, 0.0), (19, True, 0.0), (25, False, 2e-4)])
-def test_one_kernel_per_iteration_equals_two_kernel_loop(precision, nz, phase_only, ptol, monkeypatch):
+@pytest.mark.parametrize("nz,phase_only,mtol", [(25, False, 0.0), (19, True, 0.0), (25, False, 2e-3)])
+def test_one_kernel_per_iteration_equals_two_kernel_loop(precision, nz, phase_only, mtol, monkeypatch):
     """The fused loop (plane kernel + in-kernel finalize behind a grid-wide arrival barrier: one launch per iteration,
     stacks whose plane-kernel grid is resident at once) sums in the order of the two-kernel loop: bit-identical
     per-iteration statistics, stop iteration and pupils (256^2, the fixture's shape)."""
@@ -339,13 +339,13 @@ def test_one_kernel_per_iteration_equals_two_kernel_loop(precision, nz, phase_on
             monkeypatch.delenv("PYOTF_B200_PR_NO_FUSE", raising=False)
         st = eng.PRState(OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], 256, z, dev, precision)
         assert st.kernels_per_iteration() == (1 if label == "fused" else 2)
-        mse, mse_diff, pupil_diff = st.run(30, ptol, 0.0, phase_only=phase_only)
+        mse, mse_diff, pupil_diff = st.run(30, 0.0, mtol, phase_only=phase_only)
         out[label] = (np.array(mse), np.array(mse_diff), np.array(pupil_diff), st.get_pupil(0).cpu().numpy(), st.get_pupil(1).cpu().numpy())
         # a second run on the same state (PhaseRetrieval.step): the arrival counter restarts
         mse2, _, _ = st.run(3, 0.0, 0.0, phase_only=phase_only)
         out[label] += (np.array(mse2),)
     a, b = out["fused"], out["two"]
-    if ptol:
+    if mtol:
         assert len(a[0]) == len(b[0]) < 30
     for i, (x, y) in enumerate(zip(a, b)):
         if i == 2:          # pupil_diff: the per-CTA sums of |old - new|^2 are grouped differently (124 vs 32 pixels per CTA)
