@@ -392,27 +392,37 @@ def bench_other_configs(precision, rank, world, dist=None):
     out["hanser1024_cfg4"] = {"planes_per_s": 1024 / (ms * 1e-3), "ms_whole_stack": ms, "planes": 1024, "planes_per_rank": hi - lo,
                               "n_gpus": world, "achieved_GBps_per_gpu": (hi - lo) * 1024 * 1024 * es / (ms * 1e-3) / 1e9,
                               "scaling": "strong (the whole 1024-plane stack, z-sharded; max over ranks)",
-                              "note": "two-pass K1b in 64-plane chunks (outputs alternate over 2 x 256 MiB buffers)"}
+                              "note": "K1br: two register-resident passes per plane (csrc/hanser_bigsym.cuh), 64-plane calls "
+                                      "(outputs alternate over 2 x 256 MiB buffers)"}
     del outb
     torch.cuda.empty_cache()
     if rank == 0:
         # ---- config 3: SheppardPSF 256^3 (zres=190; the 200 of BASELINE.json raises ValueError in the reference) ----
         sh = SheppardPSF(wl=520, na=1.27, ni=1.33, res=100, zres=190, size=256, zsize=256, precision=precision)
 
-        def shep_step():
-            sh._attribute_changed()
-            return sh.PSFi_dev
+        NB = 8                                                # back-to-back calls per repetition (steady state)
 
-        ms = _time_gpu(shep_step, reps=4)
+        def shep_step():
+            for _ in range(NB):
+                sh._attribute_changed()
+                sh.PSFi_dev
+
+        ms = _time_gpu(shep_step, reps=4) / NB
         out["sheppard_cfg3"] = {"volumes_per_s": 1 / (ms * 1e-3), "ms_per_volume": ms,
                                 "achieved_GBps": 256 ** 3 * es / (ms * 1e-3) / 1e9,
-                                "note": "shell generator + shifted 3D inverse FFT + |.|^2 -> PSFi (replicas only across GPUs)"}
+                                "note": "shell generator + shifted 3D inverse FFT + |.|^2 -> PSFi (replicas only across GPUs); "
+                                        "8 back-to-back volumes per timed repetition"}
         # ---- config 1 epilogue: OTFi from the resident PSFi --------------------------------------------------------
         m = HanserPSF(precision=precision, **CFG1)
         psfi = m.PSFi_dev
-        ms = _time_gpu(lambda: _fft.shifted_fft_dev(psfi, axes=None, inverse=False), reps=4)
+        def otf_step():
+            for _ in range(NB):
+                _fft.shifted_fft_dev(psfi, axes=None, inverse=False)
+
+        ms = _time_gpu(otf_step, reps=4) / NB
         out["otfi_cfg1"] = {"ms": ms, "achieved_GBps": 128 * 256 * 256 * 3 * es / (ms * 1e-3) / 1e9,
-                            "note": "shifted 3D FFT of the resident 128 x 256^2 PSFi (algorithmic bytes: real read + complex write)"}
+                            "note": "shifted 3D FFT of the resident 128 x 256^2 PSFi through the Hermitian half-spectrum passes "
+                                    "(algorithmic bytes: real read + complex write); 8 back-to-back transforms per timed repetition"}
     if dist is not None:
         # OTFi of a z-sharded stack (cfg1 planes per rank, all-gather or all-to-all, pyotf_b200/_dist.py)
         from pyotf_b200 import _dist

@@ -42,8 +42,10 @@ int fft_axis_launch_l(const AxisPass& p, const void* src, void* dst, int smem_li
 }
 
 // the generic strided pass as a line functor of the register-resident kernel (fft_lines_reg.cuh):
-// line = outer * n_inner + inner, element l of a line at ((outer * L + l) * n_inner + inner)
-template <typename TIN, typename T> struct AxisFn {
+// line = outer * n_inner + inner, element l of a line at ((outer * L + l) * n_inner + inner).
+// LC = the (power-of-two) axis length at compile time; SMALL = the array has fewer than 2^31 elements: element offsets
+// inside a line are 32-bit products and the shifts are masks (the index arithmetic was half of the pass's instructions).
+template <typename TIN, typename T, int LC = 0, bool SMALL = false> struct AxisFn {
     struct Line { const TIN* in; cplx<T>* out; bool has; };
     using Acc = int;
     static constexpr int LOAD_BATCH = 8;
@@ -56,8 +58,15 @@ template <typename TIN, typename T> struct AxisFn {
     __device__ __forceinline__ bool skip() const { return false; }
     __device__ __forceinline__ cplx<T> twiddle(int k) const { return reinterpret_cast<const cplx<T>*>(p.tw)[k]; }
     __device__ __forceinline__ Line info(long long line) const {
-        const long long outer = line / p.n_inner, inner = line - outer * p.n_inner;
-        const size_t base = (size_t)outer * p.L * p.n_inner + inner;
+        size_t base;
+        if constexpr (SMALL) {
+            const unsigned ln = (unsigned)line, ni = (unsigned)p.n_inner;
+            const unsigned outer = ln / ni, inner = ln - outer * ni;
+            base = (size_t)(outer * (unsigned)p.L * ni + inner);
+        } else {
+            const long long outer = line / p.n_inner, inner = line - outer * p.n_inner;
+            base = (size_t)outer * p.L * p.n_inner + inner;
+        }
         Line d;
         d.in = src + base; d.out = dst + base;
         d.has = p.line_flags ? p.line_flags[line] != 0 : true;
@@ -69,21 +78,32 @@ template <typename TIN, typename T> struct AxisFn {
     }
     __device__ __forceinline__ cplx<T> load(const Line& d, int i) const {
         if (!d.has) return mk<T>(0, 0);
-        int l = i + p.in_shift; if (l >= p.L) l -= p.L;              // x_in[i] = src[(i + in_shift) % L]
-        return load_as_cplx<TIN, T>(d.in, (size_t)l * p.n_inner);
+        if constexpr (SMALL && LC > 0) {
+            const unsigned l = (unsigned)(i + p.in_shift) & (unsigned)(LC - 1);
+            return load_as_cplx<TIN, T>(d.in, l * (unsigned)p.n_inner);
+        } else {
+            int l = i + p.in_shift; if (l >= p.L) l -= p.L;              // x_in[i] = src[(i + in_shift) % L]
+            return load_as_cplx<TIN, T>(d.in, (size_t)l * p.n_inner);
+        }
     }
     __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v, Acc&) const {
-        int l = o + p.out_shift; if (l >= p.L) l -= p.L;             // dst[(o + out_shift) % L] = X[o]
-        d.out[(size_t)l * p.n_inner] = cscale(v, (T)p.scale);
+        if constexpr (SMALL && LC > 0) {
+            const unsigned l = (unsigned)(o + p.out_shift) & (unsigned)(LC - 1);
+            d.out[l * (unsigned)p.n_inner] = cscale(v, (T)p.scale);
+        } else {
+            int l = o + p.out_shift; if (l >= p.L) l -= p.L;             // dst[(o + out_shift) % L] = X[o]
+            d.out[(size_t)l * p.n_inner] = cscale(v, (T)p.scale);
+        }
     }
 };
 
-template <int DIR, typename TIN, typename T, int L>
-int fft_axis_reg_launch(const AxisPass& p, const void* src, void* dst, cudaStream_t s) {
-    AxisFn<TIN, T> f;
+template <int DIR, typename TIN, typename T, int L, bool SMALL>
+int fft_axis_reg_launch_s(const AxisPass& p, const void* src, void* dst, cudaStream_t s) {
+    using F = AxisFn<TIN, T, L, SMALL>;
+    F f;
     f.p = p; f.src = (const TIN*)src; f.dst = (cplx<T>*)dst;
     constexpr size_t smem = fft_lines_reg_smem<T, L>();
-    auto kern = fft_lines_reg_kernel<DIR, T, L, AxisFn<TIN, T>>;
+    auto kern = fft_lines_reg_kernel<DIR, T, L, F>;
     static thread_local bool configured[PYOTF_MAX_DEVICES] = {};
     const int dev_slot = current_device_slot();
     if (!configured[dev_slot]) {
@@ -95,6 +115,13 @@ int fft_axis_reg_launch(const AxisPass& p, const void* src, void* dst, cudaStrea
     kern<<<(unsigned)nblocks, RegPlan<L>::NT, smem, s>>>(nlines, f);
     PYOTF_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+template <int DIR, typename TIN, typename T, int L>
+int fft_axis_reg_launch(const AxisPass& p, const void* src, void* dst, cudaStream_t s) {
+    const bool small_arr = p.n_outer * (long long)p.L * p.n_inner < (1ll << 31);
+    return small_arr ? fft_axis_reg_launch_s<DIR, TIN, T, L, true>(p, src, dst, s)
+                     : fft_axis_reg_launch_s<DIR, TIN, T, L, false>(p, src, dst, s);
 }
 
 template <int DIR, typename TIN, typename T>
@@ -238,6 +265,98 @@ int rfft_z_half_launch(const void* src, void* dst, long long plane, int in_shift
     return 0;
 }
 
+// ---- contiguous-axis pass in the register mapping (the x pass of the real 3D transform) -----------------------------
+// A CTA brings LANES consecutive lines (rows of L complex values, contiguous in memory) into a shared-memory tile with an
+// odd pitch (coalesced loads, all in flight), transforms them one LANE per line exactly like fft_lines_reg_kernel
+// (radix-R1 units from the tile, one exchange, radix-R2 units back into the tile) and writes the tile out coalesced --
+// with HERM every line goes to its fftshift-ed plane and, conjugated and reversed, to its Hermitian partner (AxisPass).
+// 45 instead of 105 instructions per point of the staged generic kernel (whose index arithmetic was 58 % of its code).
+template <int DIR, typename T, int L, int LANES, bool HERM>
+__global__ void __launch_bounds__(LANES * 16) cfft_rows_kernel(AxisPass p, const cplx<T>* __restrict__ src, cplx<T>* __restrict__ dst) {
+    using P = RegPlan<L>;
+    constexpr int R1 = P::R1, R2 = P::R2, NU = 16, NT = LANES * NU, TP = L + 1, PER = LANES * L / NT;
+    static_assert(R1 <= NU && R2 <= NU && (LANES * L) % NT == 0, "plan");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);            // [L]
+    cplx<T>* Tt = tw + L;                                           // [LANES][L + 1]
+    cplx<T>* E = Tt + (size_t)LANES * TP;                           // [R1][R2][LANES]
+    const int tid = threadIdx.x, lane = tid % LANES, u = tid / LANES;
+    const size_t row0 = (size_t)blockIdx.x * LANES;
+    {
+        const cplx<T>* __restrict__ s0 = src + row0 * L;
+        cplx<T> v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) v[k] = s0[k * NT + tid];
+        const cplx<T>* __restrict__ twg = reinterpret_cast<const cplx<T>*>(p.tw);
+        for (int k = tid; k < L; k += NT) tw[k] = twg[k];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { const int e = k * NT + tid; Tt[(e / L) * TP + (e & (L - 1))] = v[k]; }
+    }
+    __syncthreads();
+    const cplx<T>* trow = Tt + (size_t)lane * TP;
+    for (int g = u; g < R2; g += NU) {
+        cplx<T> x[R1];
+        const int gs = g + p.in_shift;
+#pragma unroll
+        for (int q = 0; q < R1; ++q) x[q] = trow[(R2 * q + gs) & (L - 1)];      // x_in[i] = src[(i + in_shift) % L]
+        fft_radix<DIR, R1>(x);
+        cplx<T>* e = E + (size_t)g * LANES + lane;
+        e[0] = x[0];
+#pragma unroll
+        for (int c = 1; c < R1; ++c) {
+            const cplx<T> w = tw[(g * c) & (L - 1)];
+            e[(size_t)c * R2 * LANES] = DIR > 0 ? cmul(x[c], w) : cmulc(x[c], w);
+        }
+    }
+    __syncthreads();
+    const T scale = (T)p.scale;
+    for (int c1 = u; c1 < R1; c1 += NU) {
+        cplx<T> x[R2];
+        const cplx<T>* e = E + (size_t)c1 * R2 * LANES + lane;
+#pragma unroll
+        for (int g = 0; g < R2; ++g) x[g] = e[(size_t)g * LANES];
+        fft_radix<DIR, R2>(x);
+        cplx<T>* orow = Tt + (size_t)lane * TP;
+        const int os = c1 + p.out_shift;
+#pragma unroll
+        for (int c2 = 0; c2 < R2; ++c2) orow[(os + R1 * c2) & (L - 1)] = cscale(x[c2], scale);   // dst[(o + out_shift) % L] = X[o]
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int e = k * NT + tid, r = e / L, c = e & (L - 1);
+        const cplx<T> v = Tt[r * TP + c];
+        if constexpr (HERM) {
+            // (the launcher checks that the output has fewer than 2^31 elements: 32-bit offsets)
+            const unsigned line = (unsigned)row0 + r;
+            const unsigned kz = line >> p.herm_Yshift, ys = line & (unsigned)(p.herm_Y - 1), hz = (unsigned)p.herm_Z / 2;
+            const unsigned zs = (kz + hz) & (unsigned)(p.herm_Z - 1);
+            dst[((zs << p.herm_Yshift) + ys) * L + c] = v;
+            if (kz > 0 && kz < hz) {
+                const unsigned zm = (unsigned)p.herm_Z - zs, ym = (0u - ys) & (unsigned)(p.herm_Y - 1);
+                dst[((zm << p.herm_Yshift) + ym) * L + ((0u - c) & (unsigned)(L - 1))] = cconj(v);
+            }
+        } else {
+            dst[(row0 + r) * L + c] = v;
+        }
+    }
+}
+
+template <int DIR, typename T, int L, int LANES, bool HERM>
+int cfft_rows_launch(const AxisPass& p, const void* src, void* dst, cudaStream_t s) {
+    constexpr size_t smem = sizeof(cplx<T>) * ((size_t)L + (size_t)LANES * (L + 1) + (size_t)L * LANES);
+    auto kern = cfft_rows_kernel<DIR, T, L, LANES, HERM>;
+    static thread_local bool configured[PYOTF_MAX_DEVICES] = {};
+    const int dev_slot = current_device_slot();
+    if (!configured[dev_slot]) {
+        PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev_slot] = true;
+    }
+    kern<<<(unsigned)(p.n_outer / LANES), LANES * 16, smem, s>>>(p, (const cplx<T>*)src, (cplx<T>*)dst);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <typename T> int fft_twiddles(int L, const void** out, cudaStream_t s);
 template <int DIR, typename TIN, typename T>
 int fft_axis_launch(const AxisPass& p, const void* src, void* dst, int smem_limit, cudaStream_t s);
@@ -280,7 +399,12 @@ int rfft3_shifted_run(const void* in, void* out, long long Z, long long Y, long 
         p.in_shift = (int)((X - X / 2) % X); p.out_shift = (int)(X / 2); p.scale = 1.0; p.tw = twx; p.line_flags = nullptr;
         p.herm_Z = (int)Z; p.herm_Y = (int)Y; p.herm_Yshift = 0;
         while ((1 << p.herm_Yshift) < (int)Y) ++p.herm_Yshift;
-        rc = fft_axis_launch<-1, cplx<T>, T>(p, W, out, smem_limit, s);
+        constexpr int LN = sizeof(T) == 4 ? 16 : 8;             // lines per CTA: tile + exchange = 65 KB, three CTAs per SM
+        static const bool generic_x = getenv("PYOTF_B200_RFFT3_GENERIC_X") != nullptr;      // A/B knob: the staged kernel
+        const bool small_out = Z * Y * X < (1ll << 31) && is_pow2((int)Z);
+        if (X == 256 && !generic_x && small_out) rc = cfft_rows_launch<-1, T, 256, LN, true>(p, W, out, s);
+        else if (X == 128 && !generic_x && small_out) rc = cfft_rows_launch<-1, T, 128, LN, true>(p, W, out, s);
+        else rc = fft_axis_launch<-1, cplx<T>, T>(p, W, out, smem_limit, s);
     }
     cudaFreeAsync(W, s);
     if (!rc) *done = true;

@@ -75,7 +75,7 @@ template <typename T, int N, int M>
 int pr_plane_launch_nm(const pyotf_hanser* h, int nth, const PrPlaneArgs<T>& a, cudaStream_t s) {
     if constexpr (N == 256 && M == 64) {
         // fused finalize (one kernel per iteration): the 256^2 table variants only
-        if (a.arrive && a.dtab) return nth == 512 ? pr_plane_launch_nmt<T, N, M, true, 512, true>(a, s) : pr_plane_launch_nmt<T, N, M, true, 256, true>(a, s);
+        if (a.arrive && a.dtab && nth == 512) return pr_plane_launch_nmt<T, N, M, true, 512, true>(a, s);
     }
     if (nth == 512) {
         // the wide variant needs at least 512 / 32 = 16 warps of column work: only the 256^2 plans
@@ -164,7 +164,7 @@ template <typename T> int pr_setup(pyotf_pr* s, const void* data, int data_dtype
     // one kernel per iteration when every CTA of the plane kernel is resident at once (a grid-wide arrival barrier
     // inside the kernel replaces the finalize launch): 256^2, 64 rows per CTA, at most one CTA per SM
     const bool no_fuse = getenv("PYOTF_B200_PR_NO_FUSE") != nullptr;     // read at every create: tests compare the two loops
-    s->fuse = (!no_fuse && !s->generic && h->N == 256 && s->M == 64 && s->nparts <= sms && 2 * s->nparts >= sms) ? 1 : 0;
+    s->fuse = (!no_fuse && !s->generic && h->N == 256 && s->M == 64 && s->nth == 512 && s->nparts <= sms && 2 * s->nparts >= sms) ? 1 : 0;   // (the 256-thread CTAs of the fp64 mode finalize faster in a kernel of their own: 64.9 vs 66.8 us)
     const unsigned nb = (unsigned)((npix + 255) / 256);
     if (data_dtype == PYOTF_F32) pr_convert_data_kernel<float, T><<<nb, 256, 0, st>>>((const float*)data, (T*)s->data, npix);
     else pr_convert_data_kernel<double, T><<<nb, 256, 0, st>>>((const double*)data, (T*)s->data, npix);

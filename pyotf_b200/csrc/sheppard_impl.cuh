@@ -123,7 +123,8 @@ template <typename T> struct ShepRow : NoAcc {
 };
 
 // ---- pass 3: line = (ym, xm), axis = z --------------------------------------------------------------------
-template <typename T> struct ShepCol : NoAcc {
+// FAST: the occupied planes are given as index runs and the only output is a fresh PSFi (the scalar model's usual call)
+template <typename T, bool FAST = false> struct ShepCol : NoAcc {
     struct Line { const cplx<T>* in; cplx<T>* psfa; T* psfi; };
     ShepArgs<T> a;
     __device__ __forceinline__ cplx<T> twiddle(int k) const { return a.tw_z[k]; }
@@ -134,20 +135,26 @@ template <typename T> struct ShepCol : NoAcc {
         d.psfi = a.psfi ? a.psfi + line : nullptr;
         return d;
     }
+    // (N * N * NZ < 2^31 is checked by the launcher: plane offsets are 32-bit products)
     __device__ __forceinline__ cplx<T> load(const Line& d, int l) const {
         int zm = l + a.in_z; if (zm >= a.p.NZ) zm -= a.p.NZ;
         // planes that hold no shell voxel were never written
+        if constexpr (FAST) {
+            const bool on = (unsigned)(zm - a.band0[0]) < (unsigned)a.bandn[0] || (unsigned)(zm - a.band0[1]) < (unsigned)a.bandn[1];
+            return on ? d.in[(unsigned)zm * (unsigned)(a.p.N * a.p.N)] : mk<T>(0, 0);
+        }
         if (a.bandn[0] >= 0) {
             if ((unsigned)(zm - a.band0[0]) >= (unsigned)a.bandn[0] && (unsigned)(zm - a.band0[1]) >= (unsigned)a.bandn[1]) return mk<T>(0, 0);
         } else if (!a.planeflag[(size_t)zm * a.p.N]) {
             return mk<T>(0, 0);
         }
-        return d.in[(size_t)zm * a.p.N * a.p.N];
+        return d.in[(unsigned)zm * (unsigned)(a.p.N * a.p.N)];
     }
     __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v, int&) const {
         int zm = o + a.out_z; if (zm >= a.p.NZ) zm -= a.p.NZ;
-        const size_t off = (size_t)zm * a.p.N * a.p.N;
+        const unsigned off = (unsigned)zm * (unsigned)(a.p.N * a.p.N);
         v = cscale(v, (T)a.scale);
+        if constexpr (FAST) { d.psfi[off] = v.x * v.x + v.y * v.y; return; }
         if (d.psfa) d.psfa[off] = v;
         if (d.psfi) {
             const T I = v.x * v.x + v.y * v.y;
@@ -166,6 +173,7 @@ int sheppard_fused(const SheppardParams& p, void* psfa_out, void* psfi_out, cuda
     PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     keep_scratch_pool();
     const size_t nvox = (size_t)p.NZ * p.N * p.N;
+    PYOTF_REQUIRE(nvox < ((size_t)1 << 31), "sheppard: volumes of 2^31 voxels or more are not supported");
     cplx<T>* tmp = nullptr;
     unsigned char* planeflag = nullptr;
     PYOTF_CUDA_OK(cudaMallocAsync(&tmp, nvox * sizeof(cplx<T>), s));
@@ -214,8 +222,13 @@ int sheppard_fused(const SheppardParams& p, void* psfa_out, void* psfi_out, cuda
         rc = fftn_run<T>(tmp, tmp, 3, shape, axes, 1, 1, 0, 1, 1, s, pf);
         if (rc) break;
         a.scale = 1.0 / (double)p.NZ;
-        ShepCol<T> f3; f3.a = a;
-        rc = fft_lines_launch<1, T, false>(p.NZ, (long long)p.N * p.N, f3, smem_limit, s);
+        if (a.bandn[0] >= 0 && !a.psfa && a.psfi && !a.accumulate) {
+            ShepCol<T, true> f3; f3.a = a;
+            rc = fft_lines_launch<1, T, false>(p.NZ, (long long)p.N * p.N, f3, smem_limit, s);
+        } else {
+            ShepCol<T> f3; f3.a = a;
+            rc = fft_lines_launch<1, T, false>(p.NZ, (long long)p.N * p.N, f3, smem_limit, s);
+        }
     }
     cudaFreeAsync(planeflag, s);
     cudaFreeAsync(tmp, s);
