@@ -271,18 +271,31 @@ int rfft_z_half_launch(const void* src, void* dst, long long plane, int in_shift
 // (radix-R1 units from the tile, one exchange, radix-R2 units back into the tile) and writes the tile out coalesced --
 // with HERM every line goes to its fftshift-ed plane and, conjugated and reversed, to its Hermitian partner (AxisPass).
 // 45 instead of 105 instructions per point of the staged generic kernel (whose index arithmetic was 58 % of its code).
-template <int DIR, typename T, int L, int LANES, bool HERM>
+// BULK: the tile is brought in by one bulk asynchronous copy per line (2 KB rows, signalled through an mbarrier) and
+// the lines that go to their own position leave the same way; the tile pitch is then L + 2 (16-byte aligned rows:
+// two-way bank conflicts on the per-lane accesses instead of none) instead of L + 1.
+template <int DIR, typename T, int L, int LANES, bool HERM, bool BULK>
 __global__ void __launch_bounds__(LANES * 16) cfft_rows_kernel(AxisPass p, const cplx<T>* __restrict__ src, cplx<T>* __restrict__ dst) {
     using P = RegPlan<L>;
-    constexpr int R1 = P::R1, R2 = P::R2, NU = 16, NT = LANES * NU, TP = L + 1, PER = LANES * L / NT;
+    constexpr int R1 = P::R1, R2 = P::R2, NU = 16, NT = LANES * NU, TP = BULK ? L + 16 / (int)sizeof(cplx<T>) : L + 1, PER = LANES * L / NT;
     static_assert(R1 <= NU && R2 <= NU && (LANES * L) % NT == 0, "plan");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
     cplx<T>* tw = reinterpret_cast<cplx<T>*>(smem_raw);            // [L]
-    cplx<T>* Tt = tw + L;                                           // [LANES][L + 1]
+    cplx<T>* Tt = tw + L;                                           // [LANES][TP]
     cplx<T>* E = Tt + (size_t)LANES * TP;                           // [R1][R2][LANES]
     const int tid = threadIdx.x, lane = tid % LANES, u = tid / LANES;
     const size_t row0 = (size_t)blockIdx.x * LANES;
-    {
+    if constexpr (BULK) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) mbar_expect_tx(&bar, (unsigned)(LANES * L * sizeof(cplx<T>)));
+        if (tid < LANES) bulk_g2s(Tt + (size_t)tid * TP, src + (row0 + tid) * L, (unsigned)(L * sizeof(cplx<T>)), &bar);
+        const cplx<T>* __restrict__ twg = reinterpret_cast<const cplx<T>*>(p.tw);
+        for (int k = tid; k < L; k += NT) tw[k] = twg[k];
+        __syncthreads();                                            // twiddles (and: the expect_tx precedes every wait)
+        mbar_wait(&bar, 0);
+    } else {
         const cplx<T>* __restrict__ s0 = src + row0 * L;
         cplx<T> v[PER];
 #pragma unroll
@@ -291,8 +304,8 @@ __global__ void __launch_bounds__(LANES * 16) cfft_rows_kernel(AxisPass p, const
         for (int k = tid; k < L; k += NT) tw[k] = twg[k];
 #pragma unroll
         for (int k = 0; k < PER; ++k) { const int e = k * NT + tid; Tt[(e / L) * TP + (e & (L - 1))] = v[k]; }
+        __syncthreads();
     }
-    __syncthreads();
     const cplx<T>* trow = Tt + (size_t)lane * TP;
     for (int g = u; g < R2; g += NU) {
         cplx<T> x[R1];
@@ -321,31 +334,43 @@ __global__ void __launch_bounds__(LANES * 16) cfft_rows_kernel(AxisPass p, const
 #pragma unroll
         for (int c2 = 0; c2 < R2; ++c2) orow[(os + R1 * c2) & (L - 1)] = cscale(x[c2], scale);   // dst[(o + out_shift) % L] = X[o]
     }
+    if constexpr (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is read by the copy engine next
     __syncthreads();
+    // (the launcher checks that the output has fewer than 2^31 elements: 32-bit offsets)
+    auto out_row = [&](unsigned line, unsigned& mirror_row) -> unsigned {
+        if constexpr (HERM) {
+            const unsigned kz = line >> p.herm_Yshift, ys = line & (unsigned)(p.herm_Y - 1), hz = (unsigned)p.herm_Z / 2;
+            const unsigned zs = (kz + hz) & (unsigned)(p.herm_Z - 1);
+            mirror_row = (kz > 0 && kz < hz) ? ((((unsigned)p.herm_Z - zs) << p.herm_Yshift) + ((0u - ys) & (unsigned)(p.herm_Y - 1))) : 0xffffffffu;
+            return (zs << p.herm_Yshift) + ys;
+        } else {
+            mirror_row = 0xffffffffu;
+            return line;
+        }
+    };
+    if constexpr (BULK) {
+        if (tid < LANES) {
+            unsigned mr;
+            const unsigned orow = out_row((unsigned)row0 + tid, mr);
+            bulk_s2g(dst + (size_t)orow * L, Tt + (size_t)tid * TP, (unsigned)(L * sizeof(cplx<T>)));
+        }
+    }
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         const int e = k * NT + tid, r = e / L, c = e & (L - 1);
+        unsigned mr;
+        const unsigned orow = out_row((unsigned)row0 + r, mr);
         const cplx<T> v = Tt[r * TP + c];
-        if constexpr (HERM) {
-            // (the launcher checks that the output has fewer than 2^31 elements: 32-bit offsets)
-            const unsigned line = (unsigned)row0 + r;
-            const unsigned kz = line >> p.herm_Yshift, ys = line & (unsigned)(p.herm_Y - 1), hz = (unsigned)p.herm_Z / 2;
-            const unsigned zs = (kz + hz) & (unsigned)(p.herm_Z - 1);
-            dst[((zs << p.herm_Yshift) + ys) * L + c] = v;
-            if (kz > 0 && kz < hz) {
-                const unsigned zm = (unsigned)p.herm_Z - zs, ym = (0u - ys) & (unsigned)(p.herm_Y - 1);
-                dst[((zm << p.herm_Yshift) + ym) * L + ((0u - c) & (unsigned)(L - 1))] = cconj(v);
-            }
-        } else {
-            dst[(row0 + r) * L + c] = v;
-        }
+        if constexpr (!BULK) dst[orow * L + c] = v;
+        if (HERM && mr != 0xffffffffu) dst[mr * L + ((0u - c) & (unsigned)(L - 1))] = cconj(v);
     }
+    if constexpr (BULK) { if (tid < LANES) bulk_commit_and_wait_read(); }      // the tile must outlive the copy engine's reads
 }
 
-template <int DIR, typename T, int L, int LANES, bool HERM>
-int cfft_rows_launch(const AxisPass& p, const void* src, void* dst, cudaStream_t s) {
-    constexpr size_t smem = sizeof(cplx<T>) * ((size_t)L + (size_t)LANES * (L + 1) + (size_t)L * LANES);
-    auto kern = cfft_rows_kernel<DIR, T, L, LANES, HERM>;
+template <int DIR, typename T, int L, int LANES, bool HERM, bool BULK>
+int cfft_rows_launch_b(const AxisPass& p, const void* src, void* dst, cudaStream_t s) {
+    constexpr size_t smem = sizeof(cplx<T>) * ((size_t)L + (size_t)LANES * (L + 2) + (size_t)L * LANES);
+    auto kern = cfft_rows_kernel<DIR, T, L, LANES, HERM, BULK>;
     static thread_local bool configured[PYOTF_MAX_DEVICES] = {};
     const int dev_slot = current_device_slot();
     if (!configured[dev_slot]) {
@@ -355,6 +380,16 @@ int cfft_rows_launch(const AxisPass& p, const void* src, void* dst, cudaStream_t
     kern<<<(unsigned)(p.n_outer / LANES), LANES * 16, smem, s>>>(p, (const cplx<T>*)src, (cplx<T>*)dst);
     PYOTF_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+template <int DIR, typename T, int L, int LANES, bool HERM>
+int cfft_rows_launch(const AxisPass& p, const void* src, void* dst, cudaStream_t s) {
+    // bulk asynchronous copies for the tile (measured 4 % slower on cfg1 than LDG / STG through registers: the 16-byte
+    // aligned tile pitch costs two-way bank conflicts; kept selectable)
+    static const bool bulk = getenv("PYOTF_B200_BULK_COPY") != nullptr;
+    const bool aligned = ((size_t)src | (size_t)dst) % 16 == 0;
+    return (bulk && aligned) ? cfft_rows_launch_b<DIR, T, L, LANES, HERM, true>(p, src, dst, s)
+                                 : cfft_rows_launch_b<DIR, T, L, LANES, HERM, false>(p, src, dst, s);
 }
 
 template <typename T> int fft_twiddles(int L, const void** out, cudaStream_t s);

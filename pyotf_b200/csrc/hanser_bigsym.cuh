@@ -305,8 +305,8 @@ template <typename T> struct BigGenCfg {
     static constexpr int LANES = 8;                          // lines per CTA (one per lane of a quarter-warp)
     static constexpr int NT = 256;                           // 32 quarter-warps = the 32 unit indices of a stage
     static constexpr int EPC = 16 / (int)sizeof(T);
-    static constexpr int OQ = N / EPC + 1;                   // staging: x = EPC * m + j lives at [j][m]
-    static constexpr int OP = EPC * OQ;                      // row pitch (reals): rows land 4 banks (16 bytes) apart
+    static constexpr int OP = N + EPC;                       // staging O[row][x], rows 16 bytes (4 banks) apart: the per-lane writes of a
+                                                             // warp (8 rows x 4 consecutive x) hit 32 different banks
     static constexpr int SP = N + 1;                         // odd pitch of the pass-A transpose tile [kx][y]
     static constexpr int EC = R + 1;                         // exchange E[c1][EC][LANES]: units 4 w .. 4 w + 3 of a warp read disjoint banks
     static constexpr size_t tw_bytes() { return sizeof(cplx<T>) * (size_t)N; }
@@ -326,6 +326,7 @@ template <typename T> struct BigGenArgs {
     cplx<T>* W;               // [nzc][K][N]
     T* psfi;                  // [nzc][N][N]
     int K, H, accumulate;
+    int bulk;                 // output lines leave through bulk asynchronous copies (shared -> global) instead of STG.128
 };
 
 // first stage of a band-limited (|f| <= H < 256) 1024-point inverse transform for residue g
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(BigGenCfg<T>::NT, sizeof(T) == 4 ? 2 : 1) hans
 template <typename T>
 __global__ void __launch_bounds__(BigGenCfg<T>::NT, sizeof(T) == 4 ? 2 : 1) hanser_biggen_rows_kernel(BigGenArgs<T> a) {
     using C = BigGenCfg<T>;
-    constexpr int LANES = C::LANES, NT = C::NT, N = C::N, EPC = C::EPC, OQ = C::OQ, OP = C::OP;
+    constexpr int LANES = C::LANES, NT = C::NT, N = C::N, EPC = C::EPC, OP = C::OP;
     pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx<T>* const tws = reinterpret_cast<cplx<T>*>(smem_raw);
@@ -428,43 +429,41 @@ __global__ void __launch_bounds__(BigGenCfg<T>::NT, sizeof(T) == 4 ? 2 : 1) hans
 #pragma unroll
         for (int g = 0; g < 32; ++g) x[g] = E[(size_t)(unit * C::EC + g) * LANES + l8];
         fft32<1>(x);
-        T* const o = O + (size_t)l8 * OP + (unit % EPC) * OQ + unit / EPC;       // x = unit + 32 c2 staged as [x % EPC][x / EPC]
+        T* const o = O + (size_t)l8 * OP + unit;                  // x = unit + 32 c2
 #pragma unroll
-        for (int c2 = 0; c2 < 32; ++c2) o[(32 / EPC) * c2] = x[c2].x * x[c2].x + x[c2].y * x[c2].y;
+        for (int c2 = 0; c2 < 32; ++c2) o[32 * c2] = x[c2].x * x[c2].x + x[c2].y * x[c2].y;
+    }
+    if (!a.accumulate && a.bulk) {
+        // ---- staged rows -> fftshift-ed output lines by the copy engine: two bulk asynchronous copies per row
+        //      (x >= 512 | x < 512 swap halves), shared -> global, SASS UBLKCP ------------------------------------
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the staged rows are read by the async proxy next
+        __syncthreads();
+        if (tid < 2 * LANES) {
+            const int row = tid >> 1, half = tid & 1;
+            const int ys = (y0 + row + N / 2) & (N - 1);
+            bulk_s2g(psfi + (size_t)ys * N + (half ? 0 : N / 2), O + (size_t)row * OP + (half ? N / 2 : 0), (unsigned)(N / 2 * sizeof(T)));
+            bulk_commit_and_wait_read();                                   // the staging tile must outlive the engine's reads
+        }
+        return;
     }
     __syncthreads();
-    // ---- staged rows -> fftshift-ed output lines, 16 bytes per lane and instruction -----------------------------
-    constexpr int NCH = N / EPC / 32, NITEM = LANES * NCH, NW = NT / 32, IU = 4;
-    for (int it0 = warp; it0 < NITEM; it0 += IU * NW) {
-        T v[IU][EPC];
-#pragma unroll
-        for (int u = 0; u < IU; ++u) {
-            const int it = it0 + u * NW;
-            if (it < NITEM) {
-                const int row = it / NCH, k = it - row * NCH;
-                const T* const o = O + (size_t)row * OP;
-                const int m = ((lane + 32 * k) + N / 2 / EPC) & (N / EPC - 1);     // x = (X + 512) mod 1024
-#pragma unroll
-                for (int j = 0; j < EPC; ++j) v[u][j] = o[j * OQ + m];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < IU; ++u) {
-            const int it = it0 + u * NW;
-            if (it < NITEM) {
-                const int row = it / NCH, k = it - row * NCH;
-                const int ys = (y0 + row + N / 2) & (N - 1);
-                T* const r0 = psfi + (size_t)ys * N + (lane + 32 * k) * EPC;
-                if constexpr (EPC == 4) {
-                    float4 q = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
-                    if (a.accumulate) { const float4 p = *reinterpret_cast<const float4*>(r0); q.x += p.x; q.y += p.y; q.z += p.z; q.w += p.w; }
-                    *reinterpret_cast<float4*>(r0) = q;
-                } else {
-                    double2 q = make_double2(v[u][0], v[u][1]);
-                    if (a.accumulate) { const double2 p = *reinterpret_cast<const double2*>(r0); q.x += p.x; q.y += p.y; }
-                    *reinterpret_cast<double2*>(r0) = q;
-                }
-            }
+    // ---- staged rows -> fftshift-ed output lines, 16 bytes per lane and instruction (further polarisation components:
+    //      read-modify-write) ------------------------------------------------------------------------------------------
+    constexpr int NCH = N / EPC / 32, NITEM = LANES * NCH, NW = NT / 32;
+    for (int it = warp; it < NITEM; it += NW) {
+        const int row = it / NCH, k = it - row * NCH;
+        const int xs = (lane + 32 * k) * EPC, xu = (xs + N / 2) & (N - 1);   // output column xs holds x = (xs + 512) mod 1024
+        const int ys = (y0 + row + N / 2) & (N - 1);
+        const T* const o = O + (size_t)row * OP + xu;
+        T* const r0 = psfi + (size_t)ys * N + xs;
+        if constexpr (EPC == 4) {
+            float4 q = *reinterpret_cast<const float4*>(o);
+            if (a.accumulate) { const float4 p = *reinterpret_cast<const float4*>(r0); q.x += p.x; q.y += p.y; q.z += p.z; q.w += p.w; }
+            *reinterpret_cast<float4*>(r0) = q;
+        } else {
+            double2 q = *reinterpret_cast<const double2*>(o);
+            if (a.accumulate) { const double2 p = *reinterpret_cast<const double2*>(r0); q.x += p.x; q.y += p.y; }
+            *reinterpret_cast<double2*>(r0) = q;
         }
     }
 }
@@ -563,6 +562,8 @@ int hanser_biggen_launch(const pyotf_hanser* h, const double* z, int nz, const v
                 a.tw = (const cplx<T>*)h->tw; a.z = z + z0; a.W = W;
                 a.psfi = (T*)psfi + ((size_t)b * nz + z0) * (size_t)C::N * C::N;
                 a.K = K; a.H = H; a.accumulate = v > 0;
+                static const bool bulk = getenv("PYOTF_B200_K1BR_BULK") != nullptr;      // A/B knob (measured 2 % slower than STG.128)
+                a.bulk = bulk && ((size_t)psfi % 16 == 0) ? 1 : 0;
                 rc = bigsym_launch_pdl(ka, dim3((unsigned)nkb, (unsigned)nc), C::NT, C::smem_a(), s, a);
                 if (!rc) rc = bigsym_launch_pdl(kb, dim3((unsigned)(C::N / C::LANES), (unsigned)nc), C::NT, C::smem_b(), s, a);
             }
