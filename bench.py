@@ -242,6 +242,23 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100, extras=True):
                        "note": "the 7.6 MB working set of an iteration is L2-resident (ncu: 7.4 MB of DRAM reads per "
                                "plane-kernel launch only because ncu flushes caches), so HBM is not the binding limit: "
                                "the plane kernel is instruction-issue / latency bound on the 100 SMs its 100 CTAs occupy"}
+    # what does bind: instruction issue on the SMs the grid occupies, and the FP32 work of the transforms
+    _, winst, _ = k1_traffic("pr_" + precision)
+    us = 1e3 * best / iters
+    props = torch.cuda.get_device_properties(torch.cuda.current_device())
+    sms_used = min(st.nparts, props.multi_processor_count)
+    # 2 x nz x (K + N) transforms of N = 256 points, 5 N log2 N flops each, + ~20 flops per pixel of magnitude replacement
+    K = 2 * 55 + 1
+    nzl = hi - lo
+    flops = 2 * nzl * (K + 256) * 5 * 256 * 8 + nzl * 256 * 256 * 20
+    fp32_floor_us = flops / (props.multi_processor_count * 128 * 2 * 1.965e3) if precision == "fp32" else None
+    out["roofline"]["binding_limit"] = {
+        "fp32_floor_us": fp32_floor_us, "fp32_flops_per_iteration": flops, "frac_of_fp32_floor": (fp32_floor_us / us) if fp32_floor_us else None,
+        "warp_instructions_per_iteration": winst, "sms_used": sms_used,
+        "min_us_at_one_issue_per_cycle_on_the_sms_used": (winst / (sms_used * 4) / 1965.0) if winst else None,
+        "frac_of_issue_bound": (winst / (sms_used * 4) / 1965.0 / us) if winst else None,
+        "note": "FP32 floor: all 148 SMs at 128 FMA lanes per clock; issue bound: smsp__inst_executed.sum of the stamped ncu "
+                "capture of pr_plane_kernel on the SMs its grid occupies (one CTA per SM)"}
     if world == 1:
         # end to end through the public API: host stack in, PhaseRetrievalResult (host arrays) out
         params = dict(PR_PARAMS)

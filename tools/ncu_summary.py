@@ -45,7 +45,7 @@ WANT = [
 
 def main():
     rep = sys.argv[1]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     print(f"# ncu summary of `{rep}` (ncu --set full --clock-control none; per launch, cold-ish caches, serialised)\n")

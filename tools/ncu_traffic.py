@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Writes profiles/k1_traffic.json from ncu --set full captures of K1 (one report per precision):
 
-    python tools/ncu_traffic.py fp32=gpurun_out/k1_TAG.ncu-rep [fp64=gpurun_out/k1_f64_TAG.ncu-rep]
+    python tools/ncu_traffic.py fp32=gpurun_out/k1_TAG.ncu-rep [fp64=gpurun_out/k1_f64_TAG.ncu-rep] [pr_fp32=gpurun_out/pr_TAG.ncu-rep]
 
 DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) and warp instructions (smsp__inst_executed.sum) of the first
 hanser_sym_kernel launch in each report, stamped with the digest of the kernel sources they were built from
@@ -18,7 +18,8 @@ sys.path.insert(0, ROOT)
 
 
 def grab(rep, kernel="hanser_sym_kernel"):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep, or the `ncu -i REPORT --page raw --csv` dump of one (big reports are condensed on the GPU box)
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     for r in body:
@@ -47,7 +48,8 @@ def main():
                    "algorithmic bytes: nothing is re-read from HBM (inputs are the 0.2 MB compact tables)."}
     for a in sys.argv[1:]:
         prec, rep = a.split("=", 1)
-        out[prec] = grab(rep)
+        # pr_fp32=...: the phase-retrieval plane kernel (fixture stack), same counters (bench.py: binding_limit of K2)
+        out[prec] = grab(rep, "pr_plane_kernel") if prec.startswith("pr_") else grab(rep)
     with open(os.path.join(ROOT, "profiles", "k1_traffic.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out, indent=1))
