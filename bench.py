@@ -505,7 +505,7 @@ def k1_traffic(precision):
 
         with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("source_digest") != _build._digest():
+        if tj.get("source_digest") != _build.hot_digest():
             return None, None, "profiles/k1_traffic.json was captured from other kernel sources than this run's: not reported"
         rec = tj.get(precision) or {}
         return rec.get("dram_bytes"), rec.get("warp_instructions"), tj.get("note")

@@ -66,6 +66,23 @@ def _tu_digest(src):
     return h.hexdigest()
 
 
+def hot_digest():
+    """Digest of everything the two headline kernels are compiled from (K1s and the phase-retrieval kernels with their
+    transitive headers, the build flags): what tools/ncu_traffic.py stamps its ncu counters with, and what bench.py
+    compares before it quotes them.  Sources of other kernels do not enter."""
+    h = hashlib.sha256()
+    files = set()
+    for src in ("hanser_sym_f32.cu", "hanser_sym_f64.cu", "pr_f32.cu"):
+        files |= _deps(os.path.join(CSRC, src))
+    for f in sorted(files):
+        if f.endswith(".h"):
+            continue                                     # the C-ABI declarations do not enter the kernels
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(ARCH + FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
     stamp = LIB + ".digest"
     dig = _digest()

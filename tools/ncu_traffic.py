@@ -5,7 +5,7 @@
 
 DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) and warp instructions (smsp__inst_executed.sum) of the first
 hanser_sym_kernel launch in each report, stamped with the digest of the kernel sources they were built from
-(pyotf_b200.build._digest) and the git commit, so that bench.py only quotes them for the very same sources."""
+(pyotf_b200.build.hot_digest: K1s, the phase-retrieval kernels and their headers) and the git commit, so that bench.py only quotes them for the very same sources."""
 import csv
 import io
 import json
@@ -40,7 +40,7 @@ def grab(rep, kernel="hanser_sym_kernel"):
 def main():
     from pyotf_b200 import build
 
-    out = {"source_digest": build._digest(),
+    out = {"source_digest": build.hot_digest(),
            "commit": subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip(),
            "note": "dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of one K1 launch over the cfg1 stack, "
                    "ncu --set full (cold-ish caches, the launch alone on the GPU).  The PSFi store is absorbed by the 126 MB L2 "
