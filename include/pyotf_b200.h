@@ -262,6 +262,17 @@ int pyotf_b200_bin_lateral(const void* in_dev, int nz, int size, int factor, int
  * axes=(1, 2)) * exc with disk = (sqrt(i^2 + j^2) < radius) / count on a ceil(2 radius)|1 window; all [nz][size][size]. */
 int pyotf_b200_disk_conv_mul(const void* em_dev, const void* exc_dev, int nz, int size, double radius, void* out_dev,
                              int dtype, void* stream);
+/* BaseSIMMicroscope.model_psf, the Wiener-filtered OTF (pyotf/microscope.py:341-355): out[i] (real) =
+ * a / (a + max(a) * wiener^2) with a = |otf[i]|^2 of the complex input, or (a > 1e-16) when wiener == 0. */
+int pyotf_b200_wiener_otf(const void* otf_c_dev, long long n, double wiener, void* out_dev, int dtype, void* stream);
+/* BaseSIMMicroscope.model_psf (pyotf/microscope.py:316-401): out = psf * excitation intensity of the structured
+ * illumination (two beams at +-alpha per orientation, alpha = arcsin(na_exc / ni), plus a DC beam when dc != 0), the
+ * orientations (host array, <= 16) summed incoherently (coherent == 0; dc_suppress subtracts (2 n - 1) psf) or added
+ * coherently before squaring (lattice SIM).  psf [nz][size][size]: real, or complex when psf_is_complex (its real
+ * part is used: easy_ifft(wiener_otf).real).  Coordinates are (arange(n) - (n + 1) // 2) * res / zres. */
+int pyotf_b200_sim_psf(const void* psf_dev, int psf_is_complex, int nz, int size, double res, double zres, double ni,
+                       double wl_exc, double na_exc, const double* orientations_host, int n_orient, int coherent, int dc,
+                       int dc_suppress, void* out_dev, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -426,6 +426,45 @@ def confocal_model_psf(psf_em, psf_exc, wl, na, res, pinhole_size):
     return psf_det * psf_exc
 
 
+def sim_model_psf(psf_i, otf_i, res, zres, ni, wl_exc, na_exc, wiener, coherent, dc, dc_suppress, orientations):
+    """BaseSIMMicroscope.model_psf (pyotf/microscope.py:316-401) on the model's PSFi / OTFi ([nz, N, N])."""
+    nz, n, _ = psf_i.shape
+    x = (np.arange(n) - (n + 1) // 2) * res
+    z = (np.arange(nz) - (nz + 1) // 2) * zres
+    zz, yy, xx = z[:, None, None], x[None, :, None], x[None, None, :]
+    freq = 2 * np.pi * ni / wl_exc
+    alpha = np.arcsin(na_exc / ni)
+    if wiener is None:
+        psf = psf_i
+    else:
+        assert wiener >= 0
+        otf = abs(otf_i) ** 2
+        if wiener == 0:
+            wiener_otf = otf > 1e-16
+        else:
+            w = otf.max() * wiener ** 2
+            wiener_otf = otf / (otf + w)
+        psf = np.fft.ifftshift(np.fft.ifftn(np.fft.fftshift(wiener_otf))).real        # easy_ifft(...).real
+    if dc:
+        base_pattern = np.exp(1j * zz * freq) * np.ones(psf.shape[1:], dtype=complex)[None]
+    else:
+        base_pattern = np.zeros(psf.shape, dtype=complex)
+    if not coherent:
+        sim_psf = np.zeros_like(psf)
+    for orientation in orientations:
+        exc_pattern = base_pattern if coherent else base_pattern.copy()      # coherent: the beams of all orientations add up
+        rr = xx * np.cos(orientation) + yy * np.sin(orientation)
+        for theta in (-alpha, alpha):
+            exc_pattern += np.exp(1j * ((rr * np.sin(theta) + zz * np.cos(theta)) * freq))
+        if not coherent:
+            sim_psf += psf * (abs(exc_pattern) ** 2)
+    if coherent:
+        sim_psf = psf * (abs(exc_pattern) ** 2)
+    elif dc_suppress:
+        sim_psf -= (2 * len(orientations) - 1) * psf
+    return sim_psf
+
+
 # ----------------------------------------------------------------------------------------------
 # N3: data preparation (pyotf/utils.py:76-147, 161-201)
 # ----------------------------------------------------------------------------------------------

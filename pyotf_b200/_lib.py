@@ -56,6 +56,8 @@ PROTOTYPES = {
     "pyotf_b200_abs2_sum0": (_i, [_vp, _i, _ll, _vp, _i, _vp]),
     "pyotf_b200_bin_lateral": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "pyotf_b200_disk_conv_mul": (_i, [_vp, _vp, _i, _i, _d, _vp, _i, _vp]),
+    "pyotf_b200_wiener_otf": (_i, [_vp, _ll, _d, _vp, _i, _vp]),
+    "pyotf_b200_sim_psf": (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _d, C.POINTER(_d), _i, _i, _i, _i, _vp, _i, _vp]),
     "pyotf_b200_hanser_aberration_pupil": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "pyotf_b200_sheppard_otfa": (_i, [C.POINTER(SheppardParams), _vp, _vp, _vp]),
     "pyotf_b200_sheppard_psf": (_i, [C.POINTER(SheppardParams), _vp, _vp, _vp, _vp]),

@@ -5,12 +5,16 @@ constructor keywords, validation and cache behaviour; the arithmetic -- oversamp
 normalisation (``WidefieldMicroscope.PSF``), the pinhole convolution times the excitation PSF
 (``ConfocalMicroscope.model_psf``) and the centred 3D FFT (``OTF``) -- runs in CUDA on the stacks the PSF models
 leave in HBM.  ``PSF`` / ``OTF`` / ``model_psf`` return numpy arrays like the reference; ``PSF_dev`` / ``OTF_dev`` /
-``model_psf_dev`` give the CUDA tensors.  The apotome and SIM models are not built.
+``model_psf_dev`` give the CUDA tensors.  The SIM family (``BaseSIMMicroscope``, ``SIM2DMicroscope``,
+``SIM3DMicroscope``, ``LatticeSIMMicroscope``, pyotf/microscope.py:265-425) is built the same way: the optional Wiener
+filter of the OTF and the structured-illumination intensity are CUDA kernels on the resident stacks.  The apotome
+model is not built: its radial average comes from the un-vendored ``dphtools.utils.radial_profile``.
 
 dphtools.utils.bin_ndarray is not vendored by the reference; binning is a block sum (the default of that function),
 which after the normalisation ``psf / psf.sum()`` is indistinguishable from a block mean.
 """
 import copy
+import ctypes as C
 import logging
 
 import numpy as np
@@ -173,3 +177,99 @@ class ConfocalMicroscope(WidefieldMicroscope):
         if pixel_pinhole_radius > 1.5:
             return disk_conv_mul_dev(em, exc, pixel_pinhole_radius)
         return em * exc
+
+
+def wiener_otf_dev(otf_dev, wiener):
+    """abs(otf) ** 2 / (abs(otf) ** 2 + max * wiener ** 2), or the support (> 1e-16) for wiener == 0; real CUDA tensor."""
+    torch = _engine._torch()
+    otf_dev = otf_dev.contiguous()
+    rt = torch.float32 if otf_dev.dtype == torch.complex64 else torch.float64
+    out = torch.empty(otf_dev.shape, dtype=rt, device=otf_dev.device)
+    _lib.check(_lib.load().pyotf_b200_wiener_otf(_engine.ptr(otf_dev), int(otf_dev.numel()), float(wiener), _engine.ptr(out),
+                                                 0 if rt == torch.float32 else 1, _engine.stream_ptr()))
+    return out
+
+
+def sim_psf_dev(psf_dev, res, zres, ni, wl_exc, na_exc, orientations, coherent, dc, dc_suppress):
+    """psf * structured-illumination intensity (pyotf/microscope.py:357-401) on a CUDA stack [nz, N, N] (real, or complex:
+    its real part is used)."""
+    torch = _engine._torch()
+    psf_dev = psf_dev.contiguous()
+    cplx = psf_dev.is_complex()
+    rt = torch.float32 if psf_dev.dtype in (torch.float32, torch.complex64) else torch.float64
+    nz, n, n2 = psf_dev.shape
+    if n != n2:
+        raise ValueError("the stack must be square")
+    out = torch.empty((nz, n, n), dtype=rt, device=psf_dev.device)
+    ori = np.ascontiguousarray(np.asarray(list(orientations), dtype=np.float64))
+    _lib.check(_lib.load().pyotf_b200_sim_psf(_engine.ptr(psf_dev), int(cplx), int(nz), int(n), float(res), float(zres), float(ni),
+                                              float(wl_exc), float(na_exc), ori.ctypes.data_as(C.POINTER(C.c_double)), int(ori.size),
+                                              int(bool(coherent)), int(bool(dc)), int(bool(dc_suppress)), _engine.ptr(out),
+                                              0 if rt == torch.float32 else 1, _engine.stream_ptr()))
+    return out
+
+
+class BaseSIMMicroscope(WidefieldMicroscope):
+    """A base class for SIM and SIM like microscopes (pyotf/microscope.py:265-401)."""
+
+    na_exc = NumericProperty(attr="_na_exc", vartype=float, doc="The excitation NA")
+    wl_exc = NumericProperty(attr="_wl_exc", vartype=float, doc="The excitation wavelength")
+    coherent = NumericProperty(attr="_coherent", vartype=bool, doc="Treat the orientations coherently?")
+    dc = NumericProperty(attr="_dc", vartype=bool, doc="Include the DC component")
+    dc_suppress = NumericProperty(attr="_dc_suppress", vartype=bool, doc="Suppress the DC component")
+
+    def __init__(self, *, na_exc, wl_exc, wiener, coherent, dc, dc_suppress, orientations, **kwargs):
+        super().__init__(**kwargs)
+        if na_exc is None:
+            na_exc = self.psf_params["na"]
+        self.na_exc = na_exc
+        if wl_exc is None:
+            wl_exc = self.psf_params["wl"]
+        self.wl_exc = wl_exc
+        self.coherent = coherent
+        self.dc = dc
+        self.dc_suppress = dc_suppress
+        self.orientations = orientations
+        self.wiener = wiener
+        if self.wiener < 0:
+            raise ValueError(f"self.wiener is {self.wiener:} which should be greater than zero")
+
+    def __repr__(self):
+        return (super().__repr__()[:-1]
+                + f", na_exc={self.na_exc}, wl_exc={self.wl_exc}, wiener={self.wiener}, "
+                + f"coherent={self.coherent}, dc={self.dc}, dc_suppress={self.dc_suppress}, "
+                + f"orientations={self.orientations!r})")
+
+    @property
+    def model_psf_dev(self):
+        """Oversampled SIM PSF (pyotf/microscope.py:316-401)."""
+        if self.wiener is None:
+            psf = self.model.PSFi_dev
+        elif self.wiener >= 0:
+            # https://en.wikipedia.org/wiki/Wiener_deconvolution ; the PSF is real, the imaginary part is discarded
+            psf = _fft.shifted_fft_dev(wiener_otf_dev(self.model.OTFi_dev, self.wiener), axes=None, inverse=True)
+        else:
+            raise ValueError(f"self.wiener is {self.wiener:} which should be greater than zero")
+        return sim_psf_dev(psf, self.psf_params["res"], self.psf_params["zres"], self.psf_params["ni"], self.wl_exc, self.na_exc,
+                           self.orientations, self.coherent, self.dc, self.dc_suppress)
+
+
+class SIM2DMicroscope(BaseSIMMicroscope):
+    """A class for 2D-SIM, including optical sectioning SIM (pyotf/microscope.py:404-408)."""
+
+    def __init__(self, **kwargs):
+        super().__init__(coherent=False, dc=False, **kwargs)
+
+
+class SIM3DMicroscope(BaseSIMMicroscope):
+    """A class for 3D-SIM using multiple pattern orientations (pyotf/microscope.py:411-415)."""
+
+    def __init__(self, **kwargs):
+        super().__init__(coherent=False, dc=True, **kwargs)
+
+
+class LatticeSIMMicroscope(BaseSIMMicroscope):
+    """A class for Zeiss Lattice SIM (pyotf/microscope.py:418-425)."""
+
+    def __init__(self, **kwargs):
+        super().__init__(coherent=True, dc=True, orientations=(0, np.pi / 2), **kwargs)

@@ -139,6 +139,34 @@ def test_microscope_widefield_and_confocal(size, oversample):
         np.testing.assert_array_equal(orc.otfi(c.PSF), c.OTF)
 
 
+@pytest.mark.parametrize("kind", ["sim2d", "os-sim", "sim3d", "lattice", "sim3d-no-suppress", "sim2d-wiener0"])
+def test_microscope_sim_family(kind):
+    """N4: the oracle's restatement of BaseSIMMicroscope.model_psf (pyotf/microscope.py:316-401) against the live
+    SIM2DMicroscope / SIM3DMicroscope / LatticeSIMMicroscope, with and without the Wiener filter."""
+    refshim.load_reference()
+    from pyotf import microscope as rm
+
+    kw = dict(model="hanser", na=0.85, ni=1.0, wl=0.585, size=16, pixel_size=0.13, oversample_factor=1, vec_corr="none",
+              condition="none", na_exc=None, wl_exc=0.561, wiener=0.1, dc_suppress=True)
+    ori = (0, 2 * np.pi / 3, 4 * np.pi / 3)
+    if kind == "sim2d":
+        m = rm.SIM2DMicroscope(orientations=ori, **kw)
+    elif kind == "os-sim":
+        m = rm.SIM2DMicroscope(orientations=ori, **{**kw, "na_exc": 0.425})
+    elif kind == "sim3d":
+        m = rm.SIM3DMicroscope(orientations=ori, **kw)
+    elif kind == "lattice":
+        m = rm.LatticeSIMMicroscope(**kw)
+    elif kind == "sim3d-no-suppress":
+        m = rm.SIM3DMicroscope(orientations=ori[:2], **{**kw, "wiener": 0.5, "dc_suppress": False})
+    else:
+        m = rm.SIM2DMicroscope(orientations=ori, **{**kw, "wiener": 0})
+    got = orc.sim_model_psf(m.model.PSFi, m.model.OTFi, m.psf_params["res"], m.psf_params["zres"], m.psf_params["ni"], m.wl_exc,
+                            m.na_exc, m.wiener, m.coherent, m.dc, m.dc_suppress, m.orientations)
+    np.testing.assert_array_equal(got, m.model_psf)
+    np.testing.assert_array_equal(orc.widefield_psf(got, 1, 16), m.PSF)
+
+
 def test_data_prep_restatements(ref):
     """N3: center_data / remove_bg / prep_data_for_PR (no-resize branch) of the oracle against the live
     pyotf.utils (pyotf/utils.py:76-147, 161-201) and its doctest values (utils.py:91-114, :134-136)."""
