@@ -97,20 +97,23 @@ __global__ void __launch_bounds__(256) aberration_pupil_kernel(AberrationParams 
     const int KK = p.K * p.K;                 // real pixels; the padded layout has KR * K
     const int KKP = p.KR * p.K;
     const int pix0 = blockIdx.x * PIX;
-    for (int w = threadIdx.x; w < PIX * p.nmodes; w += blockDim.x) {
-        int j = w / PIX, q = w - j * PIX;
-        int idx = pix0 + q;
-        double val = 0.0;
-        if (idx < KK) {
-            int iy = idx / p.K, ix = idx - iy * p.K;
-            double ky = __dmul_rn((double)(p.f0 + iy), p.kstep);
-            double kx = __dmul_rn((double)(p.f0 + ix), p.kstep);
-            double kr = hypot_ref(ky, kx), phi = atan2(ky, kx);
-            double r = __dmul_rn(kr, p.wl) / p.na;              // otf.py:632
-            val = zernike_value(r, phi, zn[j], zm[j], 1);
-            if (j == 0) ideal[q] = kr <= p.diff_limit ? 1.0 : 0.0;
+    {
+        // a thread evaluates its modes j = t / PIX, t / PIX + blockDim / PIX, ... for ONE pixel (PIX divides blockDim): the
+        // polar coordinates are computed once per thread, not once per (pixel, mode)
+        const int q = threadIdx.x % PIX, idx = pix0 + q;
+        double r = 0.0, phi = 0.0;
+        bool inpix = idx < KK;
+        if (inpix) {
+            const int iy = idx / p.K, ix = idx - iy * p.K;
+            const double ky = __dmul_rn((double)(p.f0 + iy), p.kstep);
+            const double kx = __dmul_rn((double)(p.f0 + ix), p.kstep);
+            const double kr = hypot_ref(ky, kx);
+            phi = atan2(ky, kx);
+            r = __dmul_rn(kr, p.wl) / p.na;                      // otf.py:632
+            if (threadIdx.x < PIX) ideal[q] = kr <= p.diff_limit ? 1.0 : 0.0;
         }
-        Z[w] = val;
+        for (int j = threadIdx.x / PIX; j < p.nmodes; j += blockDim.x / PIX)
+            Z[j * PIX + q] = inpix ? zernike_value(r, phi, zn[j], zm[j], 1) : 0.0;
     }
     __syncthreads();
     // thread <-> (pixel q, batch lane); lanes of a warp cover consecutive pixels
@@ -124,20 +127,37 @@ __global__ void __launch_bounds__(256) aberration_pupil_kernel(AberrationParams 
             pupilc[(size_t)b * KKP + idx] = mk<T>(0, 0);
         return;
     }
-    for (int b = blockIdx.y * nbl + bl; b < p.batch; b += nbl * gridDim.y) {
-        double mag = 0.0, ph = 0.0;
+    // EB entries at a time: EB independent accumulation chains per thread (one chain of nmodes dependent DFMAs per entry
+    // left the kernel latency-bound)
+    constexpr int EB = 4;
+    const int bstep = nbl * gridDim.y;
+    for (int b0 = blockIdx.y * nbl + bl; b0 < p.batch; b0 += EB * bstep) {
+        double mag[EB], ph[EB];
+#pragma unroll
+        for (int e = 0; e < EB; ++e) { mag[e] = 0.0; ph[e] = 0.0; }
         if (p.has_mag) {
-            const double* mc = mcoefs + (size_t)b * p.nmodes;
-            for (int j = 0; j < p.nmodes; ++j) mag += Z[j * PIX + q] * mc[j];
+            for (int j = 0; j < p.nmodes; ++j) {
+                const double zj = Z[j * PIX + q];
+#pragma unroll
+                for (int e = 0; e < EB; ++e) { const int b = b0 + e * bstep; if (b < p.batch) mag[e] += zj * mcoefs[(size_t)b * p.nmodes + j]; }
+            }
         }
         if (p.has_phase) {
-            const double* pc = pcoefs + (size_t)b * p.nmodes;
-            for (int j = 0; j < p.nmodes; ++j) ph += Z[j * PIX + q] * pc[j];
+            for (int j = 0; j < p.nmodes; ++j) {
+                const double zj = Z[j * PIX + q];
+#pragma unroll
+                for (int e = 0; e < EB; ++e) { const int b = b0 + e * bstep; if (b < p.batch) ph[e] += zj * pcoefs[(size_t)b * p.nmodes + j]; }
+            }
         }
-        mag += ideal[q];                                         // otf.py:639
-        double s, c;
-        sincos(ph, &s, &c);
-        pupilc[(size_t)b * KKP + idx] = mk<T>((T)(mag * c), (T)(mag * s));
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            const int b = b0 + e * bstep;
+            if (b >= p.batch) continue;
+            const double m = mag[e] + ideal[q];                      // otf.py:639
+            double s, c;
+            sincos(ph[e], &s, &c);
+            pupilc[(size_t)b * KKP + idx] = mk<T>((T)(m * c), (T)(m * s));
+        }
     }
 }
 
