@@ -29,6 +29,7 @@ enum { PYOTF_VEC_NONE = 0, PYOTF_VEC_X = 1, PYOTF_VEC_Y = 2, PYOTF_VEC_Z = 3, PY
 enum { PYOTF_COND_NONE = 0, PYOTF_COND_SINE = 1, PYOTF_COND_HERSCHEL = 2 };
 
 int pyotf_b200_abi_version(void);
+int pyotf_b200_version(void);                 /* = pyotf_b200_abi_version (the name of SURVEY.md section 8b) */
 const char* pyotf_b200_last_error(void);
 /* sm count, max dynamic shared memory per block, compute capability of `device` */
 int pyotf_b200_device_query(int device, int* sm_count, int* smem_optin_bytes, int* cc_major, int* cc_minor);
@@ -208,6 +209,10 @@ int pyotf_b200_pr_get_pupil(const pyotf_pr_t* s, int which, void* pupil_c128_dev
 int pyotf_b200_pr_run(pyotf_pr_t* s, int max_iters, double pupil_tol, double mse_tol, int phase_only,
                       pyotf_comm_t* comm, double* mse_host, double* mse_diff_host, double* pupil_diff_host,
                       int* iters_run_host, void* stream);
+/* = pyotf_b200_pr_run (the name of SURVEY.md section 8b) */
+int pyotf_b200_pr_iterate(pyotf_pr_t* s, int max_iters, double pupil_tol, double mse_tol, int phase_only,
+                          pyotf_comm_t* comm, double* mse_host, double* mse_diff_host, double* pupil_diff_host,
+                          int* iters_run_host, void* stream);
 
 /* z-sharded phase retrieval without a collective library call per iteration: every rank exports a small window
  * through CUDA IPC and maps the windows of all other ranks of the box.  Each iteration, CTA b of a rank's finalize
@@ -249,6 +254,10 @@ int pyotf_b200_comm_allreduce_f64(pyotf_comm_t* c, double* buf_dev, long long n,
  * shift_out = 1 give easy_fft / easy_ifft; 0/0 is the plain transform. */
 int pyotf_b200_fftn(const void* in_dev, void* out_dev, int ndim, const long long* shape, const int* axes, int naxes,
                     int inverse, int real_in, int shift_in, int shift_out, int dtype, void* stream);
+/* easy_fft (direction < 0) / easy_ifft (direction > 0) of a C-contiguous [nz][ny][nx] array over all three axes
+ * (pyotf/utils.py:15-22): pyotf_b200_fftn with ndim = naxes = 3 and both shifts (the form of SURVEY.md section 8b). */
+int pyotf_b200_fft3d_shifted(const void* in_dev, void* out_dev, int nz, int ny, int nx, int direction, int real_in,
+                             int dtype, void* stream);
 /* out[i] = sum_v |a[v][i]|^2  (BasePSF.PSFi from an existing PSFa, otf.py:204-207) */
 int pyotf_b200_abs2_sum0(const void* a_dev, int nvec, long long n, void* out_dev, int dtype, void* stream);
 

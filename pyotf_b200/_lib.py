@@ -37,6 +37,7 @@ _vp, _i, _ll, _ip, _d = C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_int), C
 # name -> (restype, argtypes); every symbol include/pyotf_b200.h declares
 PROTOTYPES = {
     "pyotf_b200_abi_version": (_i, []),
+    "pyotf_b200_version": (_i, []),
     "pyotf_b200_last_error": (C.c_char_p, []),
     "pyotf_b200_device_query": (_i, [_i, _ip, _ip, _ip, _ip]),
     "pyotf_b200_hanser_create": (_i, [C.POINTER(HanserParams), _vp, C.POINTER(_vp)]),
@@ -54,6 +55,7 @@ PROTOTYPES = {
     "pyotf_b200_zernike_gram": (_i, [_vp, _vp, _ll, _i, _i, _vp, _vp]),
     "pyotf_b200_fftn": (_i, [_vp, _vp, _i, C.POINTER(_ll), _ip, _i, _i, _i, _i, _i, _i, _vp]),
     "pyotf_b200_abs2_sum0": (_i, [_vp, _i, _ll, _vp, _i, _vp]),
+    "pyotf_b200_fft3d_shifted": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pyotf_b200_bin_lateral": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "pyotf_b200_disk_conv_mul": (_i, [_vp, _vp, _i, _i, _d, _vp, _i, _vp]),
     "pyotf_b200_wiener_otf": (_i, [_vp, _ll, _d, _vp, _i, _vp]),
@@ -70,6 +72,7 @@ PROTOTYPES = {
     "pyotf_b200_pr_set_pupil": (_i, [_vp, _vp, _vp]),
     "pyotf_b200_pr_get_pupil": (_i, [_vp, _i, _vp, _vp]),
     "pyotf_b200_pr_run": (_i, [_vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _ip, _vp]),
+    "pyotf_b200_pr_iterate": (_i, [_vp, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _ip, _vp]),
     "pyotf_b200_pr_window_alloc": (_i, [_vp, _i, _vp]),
     "pyotf_b200_pr_window_open": (_i, [_vp, _vp, _i, _i]),
     "pyotf_b200_unwrap_phase_2d": (_i, [_vp, _vp, _i, _i]),

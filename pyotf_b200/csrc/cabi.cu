@@ -75,6 +75,7 @@ static void sheppard_generate(const SheppardParams& p, void* otfa, unsigned char
 extern "C" {
 
 int pyotf_b200_abi_version(void) { return PYOTF_B200_ABI_VERSION; }
+int pyotf_b200_version(void) { return PYOTF_B200_ABI_VERSION; }          // the name SURVEY.md section 8(b) lists
 const char* pyotf_b200_last_error(void) { return g_last_error.c_str(); }
 
 int pyotf_b200_device_query(int device, int* sm_count, int* smem_optin_bytes, int* cc_major, int* cc_minor) {
@@ -481,6 +482,17 @@ int pyotf_b200_pr_get_pupil(const pyotf_pr_t* s, int which, void* out, void* str
 
 int pyotf_b200_pr_run(pyotf_pr_t* s, int max_iters, double pupil_tol, double mse_tol, int phase_only,
                       pyotf_comm_t* comm, double* mse_host, double* mse_diff_host, double* pupil_diff_host,
+                      int* iters_run_host, void* stream);
+// the name SURVEY.md section 8(b) lists for the loop entry
+int pyotf_b200_pr_iterate(pyotf_pr_t* s, int max_iters, double pupil_tol, double mse_tol, int phase_only,
+                          pyotf_comm_t* comm, double* mse_host, double* mse_diff_host, double* pupil_diff_host,
+                          int* iters_run_host, void* stream) {
+    return pyotf_b200_pr_run(s, max_iters, pupil_tol, mse_tol, phase_only, comm, mse_host, mse_diff_host, pupil_diff_host,
+                             iters_run_host, stream);
+}
+
+int pyotf_b200_pr_run(pyotf_pr_t* s, int max_iters, double pupil_tol, double mse_tol, int phase_only,
+                      pyotf_comm_t* comm, double* mse_host, double* mse_diff_host, double* pupil_diff_host,
                       int* iters_run_host, void* stream) {
     PYOTF_REQUIRE(s, "pr_run: null handle");
     PYOTF_REQUIRE(max_iters > 0, "pr_run: Must have at least one iteration");
@@ -508,6 +520,15 @@ int pyotf_b200_fftn(const void* in, void* out, int ndim, const long long* shape,
     return dtype == PYOTF_F32
                ? fftn_run<float>(in, out, ndim, shape, axes, naxes, inverse, real_in, shift_in, shift_out, s)
                : fftn_run<double>(in, out, ndim, shape, axes, naxes, inverse, real_in, shift_in, shift_out, s);
+}
+
+// the 3D convenience form SURVEY.md section 8(b) lists: easy_fft (direction < 0) / easy_ifft (direction > 0) of a
+// [nz][ny][nx] array over all three axes (pyotf/utils.py:15-22; OTFi / OTFa / Sheppard PSFa)
+int pyotf_b200_fft3d_shifted(const void* in, void* out, int nz, int ny, int nx, int direction, int real_in, int dtype, void* stream) {
+    PYOTF_REQUIRE(nz > 0 && ny > 0 && nx > 0 && direction != 0, "fft3d_shifted: bad size / direction");
+    const long long shape[3] = {nz, ny, nx};
+    const int axes[3] = {0, 1, 2};
+    return pyotf_b200_fftn(in, out, 3, shape, axes, 3, direction > 0 ? 1 : 0, real_in, 1, 1, dtype, stream);
 }
 
 int pyotf_b200_abs2_sum0(const void* a, int nvec, long long n, void* out, int dtype, void* stream) {
