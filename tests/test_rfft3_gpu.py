@@ -39,3 +39,20 @@ def test_matches_generic_passes_on_cfg1():
         m = HanserPSF(precision=prec, **kw)
         psfi = orc.psfi(orc.hanser_psfa(kw["wl"], kw["na"], kw["ni"], kw["res"], 256, m.zrange, "none", "sine"))
         assert rel_l2(m.OTFi, orc.otfi(psfi)) <= tol
+
+
+def test_fft3d_shifted_entry_point():
+    """pyotf_b200_fft3d_shifted (the 3D form SURVEY.md section 8b lists): easy_fft / easy_ifft over all three axes."""
+    import torch
+
+    from pyotf_b200 import _engine, _lib
+
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((16, 32, 64)) + 1j * rng.standard_normal((16, 32, 64))
+    x = torch.as_tensor(a, device="cuda")
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    for direction, ref in ((-1, np.fft.fftshift(np.fft.fftn(np.fft.ifftshift(a)))), (1, np.fft.ifftshift(np.fft.ifftn(np.fft.fftshift(a))))):
+        _lib.check(lib.pyotf_b200_fft3d_shifted(_engine.ptr(x), _engine.ptr(out), 16, 32, 64, direction, 0, 1, _engine.stream_ptr()))
+        assert rel_l2(out.cpu().numpy(), ref) <= 1e-12
+    assert lib.pyotf_b200_version() == lib.pyotf_b200_abi_version()
