@@ -603,6 +603,19 @@ def measure_k1(precision, args, rank, world, local, dist, sample_clocks):
         ms = e0.elapsed_time(e1)
         serial_ms = ms if serial_ms is None else min(serial_ms, ms)
     serial_ms = allmax(serial_ms) / args.steps
+    # context for the roofline: what a plain memset of the very same output buffers costs (cudaMemsetAsync through
+    # torch's zero_(), same rotation over the ring, same K launches per repetition) -- a write-only stream of this
+    # granularity does not reach the copy bandwidth MEASURED_PEAKS.json quotes
+    memset_ms = None
+    for _ in range(20):
+        e0.record(stream)
+        for i in range(args.steps):
+            outs[i % ring].zero_()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        memset_ms = ms if memset_ms is None else min(memset_ms, ms)
+    memset_ms /= args.steps
 
     # ---- e2e through the public API: host zrange in, host PSFi (numpy) out, every step ----
     model = HanserPSF(precision=precision, **CFG1)
@@ -641,6 +654,10 @@ def measure_k1(precision, args, rank, world, local, dist, sample_clocks):
                      "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                      "kernel": "hanser_sym_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                      "binding_limit": binding,
+                     "memset_of_the_same_buffers": {
+                         "ms_per_step": memset_ms, "achieved": alg_bytes / (memset_ms * 1e-3) / 1e9,
+                         "note": "torch zero_() (cudaMemsetAsync) of the same output ring, K back-to-back launches: the "
+                                 "write-only stream a kernel that computes nothing would produce"},
                      "device_z_serialized": {
                          "ms_per_step": serial_ms, "planes_per_s": nz * world / (serial_ms * 1e-3),
                          "achieved": alg_bytes / (serial_ms * 1e-3) / 1e9,

@@ -164,6 +164,10 @@ template <typename T> struct HanserArgs {
     long long pupil_stride;   // elements between pupils in pupilc (0 = shared)
     int z_in_params;          // plane positions are in zv (host-side zrange, <= PYOTF_Z_PARAM_MAX planes), z unused
     double zv[PYOTF_Z_PARAM_MAX];
+    // K1s only (default model): PSFi(-z) == PSFi(z), so planes at +-z are computed once and stored twice.  CTA c of the
+    // npair launched per stack computes plane pa[c] and stores it to planes pa[c] and pb[c] (pb[c] == pa[c]: no partner).
+    int npair;                // 0: no pairing, one CTA per plane
+    unsigned char pa[PYOTF_Z_PARAM_MAX], pb[PYOTF_Z_PARAM_MAX];
 };
 
 template <int N, int M, typename T, int NTHREADS = 256> struct HanserSmem {

@@ -159,7 +159,11 @@ __global__ void __launch_bounds__(SymCfg<T, NG, NS>::NT, (NG == 1 && sizeof(T) =
     const int grp = NG == 1 ? 0 : (storer ? (warp - C::NWC) / NS : warp / 9);
     const int sw = storer ? (warp - C::NWC) % NS : 0;       // which of the group's store warps
     const int wi = storer ? 9 : warp - 9 * grp;             // residue g (first stages) / c1 (second stages)
-    const int plane = blockIdx.x;
+    // planes at +-z of the default model have the same intensity (the defocus factors are complex conjugates, the pupil
+    // is real and even): computed once, stored to both
+    const int plane = a.npair ? a.pa[blockIdx.x] : blockIdx.x;
+    const int plane2 = a.npair ? a.pb[blockIdx.x] : plane;
+    const bool dup = plane2 != plane;
     const double z = a.z_in_params ? a.zv[plane] : a.z[plane];
     SYM_MARK(14); SYM_MARK(0);
     const bool x12z = 64 - 8 > H;                           // f = 16*12 + g - 256 is outside the band for every g <= 8
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(SymCfg<T, NG, NS>::NT, (NG == 1 && sizeof(T) =
     }
     SYM_MARK(2);
     T* const psfi = a.psfi + ((size_t)blockIdx.y * a.nz + plane) * (size_t)C::N * C::N;
+    T* const psfi2 = a.psfi + ((size_t)blockIdx.y * a.nz + plane2) * (size_t)C::N * C::N;
 
     if (storer) {
         // ---- store warp of group grp: staged 32-row blocks -> rows y and 256 - y (fftshift-ed positions), 16 bytes
@@ -270,19 +275,26 @@ __global__ void __launch_bounds__(SymCfg<T, NG, NS>::NT, (NG == 1 && sizeof(T) =
 #pragma unroll
                 for (int u = 0; u < RU; ++u) {
                     const int yy = 32 * rb + i0 + u;
-                    T* const r0 = psfi + (size_t)(yy + 128) * C::N;
-                    T* const r1 = psfi + (size_t)(128 - yy) * C::N;
+                    const size_t o0 = (size_t)(yy + 128) * C::N, o1 = (size_t)(128 - yy) * C::N;
 #pragma unroll
                     for (int k = 0; k < NCH; ++k) {
                         const int xs = (lane + 32 * k) * EPC;
                         if constexpr (EPC == 4) {
                             const float4 q = make_float4(v[u][k][0], v[u][k][1], v[u][k][2], v[u][k][3]);
-                            *reinterpret_cast<float4*>(r0 + xs) = q;
-                            if (yy != 0) *reinterpret_cast<float4*>(r1 + xs) = q;
+                            *reinterpret_cast<float4*>(psfi + o0 + xs) = q;
+                            if (yy != 0) *reinterpret_cast<float4*>(psfi + o1 + xs) = q;
+                            if (dup) {
+                                *reinterpret_cast<float4*>(psfi2 + o0 + xs) = q;
+                                if (yy != 0) *reinterpret_cast<float4*>(psfi2 + o1 + xs) = q;
+                            }
                         } else {
                             const double2 q = make_double2(v[u][k][0], v[u][k][1]);
-                            *reinterpret_cast<double2*>(r0 + xs) = q;
-                            if (yy != 0) *reinterpret_cast<double2*>(r1 + xs) = q;
+                            *reinterpret_cast<double2*>(psfi + o0 + xs) = q;
+                            if (yy != 0) *reinterpret_cast<double2*>(psfi + o1 + xs) = q;
+                            if (dup) {
+                                *reinterpret_cast<double2*>(psfi2 + o0 + xs) = q;
+                                if (yy != 0) *reinterpret_cast<double2*>(psfi2 + o1 + xs) = q;
+                            }
                         }
                     }
                 }
@@ -343,10 +355,10 @@ __global__ void __launch_bounds__(SymCfg<T, NG, NS>::NT, (NG == 1 && sizeof(T) =
     __syncthreads();
     // output row 0 (y = 128): the transpose of column x = 128
     if (warp == C::NWC) {
-        T* const r0 = psfi;
         for (int xs = lane; xs < 256; xs += 32) {
             const int ax = xs < 128 ? 128 - xs : xs - 128;
-            r0[xs] = L128[ax];
+            psfi[xs] = L128[ax];
+            if (dup) psfi2[xs] = L128[ax];
         }
         // output disjoint from every launch that may still be running: only completion has to stay in stream order
         if (a.overlap == 2) pdl_wait();
@@ -405,7 +417,7 @@ int hanser_launch_sym256(const HanserArgs<T>& a, int batch, int smem_limit, cuda
         if (fresh && !no_free) aa.overlap = 2;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)a.nz, (unsigned)batch); cfg.blockDim = dim3(C::NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)(aa.npair ? aa.npair : a.nz), (unsigned)batch); cfg.blockDim = dim3(C::NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -416,7 +428,31 @@ int hanser_launch_sym256(const HanserArgs<T>& a, int batch, int smem_limit, cuda
     return 0;
 }
 
-template <typename T> int hanser_sym_launch(const HanserArgs<T>& a, int batch, int smem_limit, cudaStream_t s, bool* done) {
+// +-z pairing (host-side zrange only: the positions are known here).  Exact negatives only; z == 0 has no partner.
+template <typename T> void sym_pair_planes(HanserArgs<T>& aa) {
+    aa.npair = 0;
+    // default: on in the fp64 mode (compute-bound: 16.8 -> 13.4 us per cfg1 stack), off in the fp32 mode (already bound by
+    // the store stream: 7.6 vs 7.3 us).  PYOTF_B200_K1_ZSYM=1 / 0 forces it (read at every launch: the tests use both).
+    const char* e = getenv("PYOTF_B200_K1_ZSYM");
+    const bool on = e ? atoi(e) != 0 : sizeof(T) == 8;
+    if (!aa.z_in_params || !on || aa.nz > PYOTF_Z_PARAM_MAX) return;
+    bool used[PYOTF_Z_PARAM_MAX] = {};
+    int np = 0;
+    for (int i = 0; i < aa.nz; ++i) {
+        if (used[i]) continue;
+        used[i] = true;
+        int partner = i;
+        if (aa.zv[i] != 0.0)
+            for (int j = i + 1; j < aa.nz; ++j)
+                if (!used[j] && aa.zv[j] == -aa.zv[i]) { partner = j; used[j] = true; break; }
+        aa.pa[np] = (unsigned char)i; aa.pb[np] = (unsigned char)partner; ++np;
+    }
+    if (np < aa.nz) aa.npair = np;                      // at least one pair: launch one CTA per pair / single
+}
+
+template <typename T> int hanser_sym_launch(const HanserArgs<T>& a_in, int batch, int smem_limit, cudaStream_t s, bool* done) {
+    HanserArgs<T> a = a_in;
+    sym_pair_planes(a);
     // one 9-warp group + two store warps per CTA; fp32: two CTAs per SM, so the stores of one plane overlap the
     // transforms of the next.  (Tuning knobs: PYOTF_B200_K1_SYM_NG=2 = two groups in one CTA per SM (fp32),
     // PYOTF_B200_K1_SYM_NS=1 = one store warp.)
@@ -424,6 +460,12 @@ template <typename T> int hanser_sym_launch(const HanserArgs<T>& a, int batch, i
     if constexpr (sizeof(T) == 4) {
         static const int ng = [] { const char* e = getenv("PYOTF_B200_K1_SYM_NG"); return e ? atoi(e) : 1; }();
         if (ng == 2) return hanser_launch_sym256<T, 2, 1>(a, batch, smem_limit, s, done);
+    }
+    if constexpr (sizeof(T) == 4) {
+        // paired planes: every staged block is stored twice, four store warps keep up with the transform warps
+        // (416 threads, 78 registers: still two CTAs per SM)
+        static const int nsp = [] { const char* e = getenv("PYOTF_B200_K1_SYM_NS_PAIRED"); return e ? atoi(e) : 4; }();
+        if (a.npair && nsp == 4) return hanser_launch_sym256<T, 1, 4>(a, batch, smem_limit, s, done);
     }
     if (ns == 2) return hanser_launch_sym256<T, 1, 2>(a, batch, smem_limit, s, done);
     return hanser_launch_sym256<T, 1, 1>(a, batch, smem_limit, s, done);

@@ -304,3 +304,37 @@ def test_whole_plane_kernel_cfg1_and_overlapping_launches(precision):
     r2 = orc.psfi(orc.hanser_psfa(wl, na, ni, res, size, z2))
     assert rel_l2(h.psf(z2)[1][0].cpu().numpy(), r2) <= TOL[precision]
     assert rel_l2(h.psf(eng.to_device_f64(z2))[1][0].cpu().numpy(), r2) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("paired", [True, False])
+def test_whole_plane_kernel_z_pairing(precision, paired, monkeypatch):
+    """K1s can compute planes at +-z once and store them twice (PSFi(-z) == PSFi(z) for the default model; the default
+    in the fp64 mode, PYOTF_B200_K1_ZSYM=1/0 forces it on / off): mixed stacks with pairs, singles, z = 0, duplicated
+    positions and unsorted order, every plane against the oracle, planes of equal |z| equal to rounding, and against the
+    same positions computed one plane per call (no partner: the ordinary path)."""
+    import torch
+
+    from oracle import pyotf_oracle as orc
+    from pyotf_b200 import _engine as eng
+
+    monkeypatch.setenv("PYOTF_B200_K1_ZSYM", "1" if paired else "0")
+    wl, na, ni, res, size = 520, 0.85, 1.0, 130, 256
+    h = eng.hanser_handle(wl, na, ni, res, size, "none", "sine", precision, -1)
+    for z in (np.array([-600.0, -300.0, 0.0, 300.0, 450.0, 600.0, 300.0]),
+              np.array([1500.0, -40.0, 40.0, -1500.0, 0.0, 0.0, 7.5]),
+              np.array([-250.0, 250.0])):
+        ref = orc.psfi(orc.hanser_psfa(wl, na, ni, res, size, z))
+        p = h.psf(z)[1][0].cpu().numpy()
+        for i in range(len(z)):
+            assert rel_l2(p[i], ref[i]) <= TOL[precision], (z, i)
+        for i in range(len(z)):
+            for j in range(i + 1, len(z)):
+                if abs(z[i]) == abs(z[j]):
+                    assert rel_l2(p[i], p[j]) <= TOL[precision] / 10
+        if paired:
+            np.testing.assert_array_equal(p[0], p[list(z).index(-z[0])])      # the first pair shares one computation
+        single = np.stack([h.psf(np.array([zi]))[1][0, 0].cpu().numpy() for zi in z])
+        for i in range(len(z)):
+            assert rel_l2(single[i], p[i]) <= TOL[precision] / 10
+    torch.cuda.synchronize()
