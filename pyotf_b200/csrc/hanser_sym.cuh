@@ -140,7 +140,9 @@ template <int N> __device__ __forceinline__ void sym_bar_arrive(int id) {
     }
 }
 
-template <typename T, int NG, int NS>
+// DUP: the launch pairs planes at +-z (HanserArgs::npair): a compile-time variant, so that the store loop of the
+// ordinary launch -- the bottleneck of the fp32 mode -- carries no extra predicate
+template <typename T, int NG, int NS, bool DUP = false>
 __global__ void __launch_bounds__(SymCfg<T, NG, NS>::NT, (NG == 1 && sizeof(T) == 4) ? 2 : 1) hanser_sym_kernel(HanserArgs<T> a, int t_off) {
     using C = SymCfg<T, NG, NS>;
     constexpr int NT = C::NT, UP = C::UP, OP = C::OP, OQ = C::OQ, EPC = C::EPC, NBUF = C::NBUF, NPASS = 4 / NG;
@@ -161,9 +163,9 @@ __global__ void __launch_bounds__(SymCfg<T, NG, NS>::NT, (NG == 1 && sizeof(T) =
     const int wi = storer ? 9 : warp - 9 * grp;             // residue g (first stages) / c1 (second stages)
     // planes at +-z of the default model have the same intensity (the defocus factors are complex conjugates, the pupil
     // is real and even): computed once, stored to both
-    const int plane = a.npair ? a.pa[blockIdx.x] : blockIdx.x;
-    const int plane2 = a.npair ? a.pb[blockIdx.x] : plane;
-    const bool dup = plane2 != plane;
+    const int plane = DUP ? a.pa[blockIdx.x] : blockIdx.x;
+    const int plane2 = DUP ? a.pb[blockIdx.x] : plane;
+    const bool dup = DUP && plane2 != plane;
     const double z = a.z_in_params ? a.zv[plane] : a.z[plane];
     SYM_MARK(14); SYM_MARK(0);
     const bool x12z = 64 - 8 > H;                           // f = 16*12 + g - 256 is outside the band for every g <= 8
@@ -391,7 +393,7 @@ inline bool sym_output_is_fresh(int dev, cudaStream_t s, const void* out, size_t
 }
 
 // K1s (hanser_sym.cuh): one CTA per plane, scalar model with the ideal pupil at N = 256, PSFi only
-template <typename T, int NG, int NS>
+template <typename T, int NG, int NS, bool DUP = false>
 int hanser_launch_sym256(const HanserArgs<T>& a, int batch, int smem_limit, cudaStream_t s, bool* done) {
     using C = SymCfg<T, NG, NS>;
     *done = false;
@@ -399,7 +401,7 @@ int hanser_launch_sym256(const HanserArgs<T>& a, int batch, int smem_limit, cuda
     size_t t_off = 0, smem = 0;
     sym_layout<T, NG, NS>(NC, &t_off, &smem);
     if (smem > (size_t)smem_limit) return 0;          // the caller falls back to the generic fused kernel
-    auto kern = hanser_sym_kernel<T, NG, NS>;
+    auto kern = hanser_sym_kernel<T, NG, NS, DUP>;
     static thread_local size_t configured[PYOTF_MAX_DEVICES] = {};
     const int dev_slot = current_device_slot();
     if (smem > configured[dev_slot]) {
@@ -417,7 +419,7 @@ int hanser_launch_sym256(const HanserArgs<T>& a, int batch, int smem_limit, cuda
         if (fresh && !no_free) aa.overlap = 2;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(aa.npair ? aa.npair : a.nz), (unsigned)batch); cfg.blockDim = dim3(C::NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)(DUP ? aa.npair : a.nz), (unsigned)batch); cfg.blockDim = dim3(C::NT); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -461,12 +463,7 @@ template <typename T> int hanser_sym_launch(const HanserArgs<T>& a_in, int batch
         static const int ng = [] { const char* e = getenv("PYOTF_B200_K1_SYM_NG"); return e ? atoi(e) : 1; }();
         if (ng == 2) return hanser_launch_sym256<T, 2, 1>(a, batch, smem_limit, s, done);
     }
-    if constexpr (sizeof(T) == 4) {
-        // paired planes: every staged block is stored twice, four store warps keep up with the transform warps
-        // (416 threads, 78 registers: still two CTAs per SM)
-        static const int nsp = [] { const char* e = getenv("PYOTF_B200_K1_SYM_NS_PAIRED"); return e ? atoi(e) : 4; }();
-        if (a.npair && nsp == 4) return hanser_launch_sym256<T, 1, 4>(a, batch, smem_limit, s, done);
-    }
+    if (a.npair) return hanser_launch_sym256<T, 1, 2, true>(a, batch, smem_limit, s, done);     // planes at +-z: one CTA per pair
     if (ns == 2) return hanser_launch_sym256<T, 1, 2>(a, batch, smem_limit, s, done);
     return hanser_launch_sym256<T, 1, 1>(a, batch, smem_limit, s, done);
 }
