@@ -94,7 +94,10 @@ def psqrt(data):
 def slice_maker(centers, widths):
     """Slices of ``widths`` centred on ``centers`` (clean-room stand-in for dphtools.slice_maker).
 
-    ``widths`` may be a scalar (applied to every axis).  Starts are clipped at 0.
+    ``widths`` may be a scalar (applied to every axis).  Starts are clipped at 0 and the window then keeps its full
+    width (``slice(0, w)``).  UNPINNED: dphtools is not vendored by the reference, so edge-clipped windows could not be
+    compared with the original (which may return a shorter window there); windows that fit are unambiguous and are
+    what the reference's own shape / centre tests exercise (tests/test_api_gpu.py).
     """
     centers = np.atleast_1d(centers)
     widths = np.broadcast_to(np.atleast_1d(widths), centers.shape)
@@ -113,7 +116,8 @@ def fft_pad(data, newshape, mode="constant"):
     """Pad ``data`` symmetrically (FFT-centre preserving) up to ``newshape``.
 
     Clean-room stand-in for dphtools.utils.fft_pad: the element at index ``n // 2`` of every
-    axis stays at index ``new_n // 2``.
+    axis stays at index ``new_n // 2``.  UNPINNED for the same reason as ``slice_maker``; shrinking raises instead of
+    cropping (``prep_data_for_PR`` crops through ``slice_maker`` before it pads).
     """
     data = np.asarray(data)
     pads = []
