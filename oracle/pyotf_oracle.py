@@ -498,12 +498,15 @@ def _fft_pad_constant(data, newshape):
 
 
 def _slice_maker(centers, width):
-    """Stand-in for dphtools.utils.slice_maker (un-vendored; PARITY UNPINNED): start = centre - width // 2 clipped at 0,
-    stop = start + width."""
+    """Stand-in for dphtools.utils.slice_maker (un-vendored; PARITY UNPINNED): start = centre - width // 2,
+    stop = start + width, only the start clipped at 0 (a window over the lower edge is shorter)."""
     out = []
     for c in centers:
-        lo = max(int(c) - int(width) // 2, 0)
-        out.append(slice(lo, lo + int(width)))
+        lo = int(c) - int(width) // 2
+        hi = lo + int(width)
+        if hi <= 0:
+            lo, hi = 0, 0
+        out.append(slice(max(lo, 0), hi))
     return tuple(out)
 
 

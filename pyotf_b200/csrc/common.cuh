@@ -85,6 +85,7 @@ struct pyotf_pr {
     long long nz_total = 0;         // planes over all ranks of a z-sharded retrieval
     int cur = 0, applied = 0;       // pupil buffer holding the final / the last applied pupil
     int launched = 0;               // iterations enqueued by the last run
+    int kernel_launches = 0;        // fused loop: plane-kernel launches of the last run (each runs up to 8 iterations)
     double* z = nullptr;            // [nz]
     void* data = nullptr;           // [nz][N][N]
     void* pupil[2] = {nullptr, nullptr};   // [KR][K] complex
@@ -105,8 +106,8 @@ struct pyotf_pr {
     void* peer[pyotf::PYOTF_MAX_PEERS] = {};   // every rank's window as mapped here (peer[win_rank] == win)
     int win_rank = 0, win_world = 0, win_alloc_world = 0;
     long long epoch_base = 0;       // epochs are monotonic over the life of the window
-    int* h_flags = nullptr;         // pinned: early-stop polling
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int* h_prog = nullptr;          // pinned, mapped: [0] stopped, [1] iterations finished (written by the kernels)
+    void* d_prog = nullptr;         // its device address
 };
 
 namespace pyotf {

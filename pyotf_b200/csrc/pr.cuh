@@ -44,7 +44,19 @@ struct PrFinalArgs {
     double npix_total;      // nz_total * N * N   (mean of the squared error)
     double nz_total;        // planes over all ranks (mean over z of the new pupils)
     double pupil_tol, mse_tol;
+    // pinned host words the deciding block writes over PCIe: [0] = PrState::stopped, [1] = iterations finished.  The
+    // host follows the loop through them without putting a copy or an event between the launches (a device-to-host
+    // copy every 8 iterations left the GPU idle for ~18 us each time: 2.3 us per iteration on the fixture).
+    int* host_prog;
 };
+
+__device__ __forceinline__ void pr_publish_progress(int* host_prog, int done, int stopped) {
+    if (!host_prog) return;
+    volatile int* hp = host_prog;
+    hp[1] = done;
+    if (stopped) hp[0] = stopped;
+    __threadfence_system();
+}
 
 template <typename T> struct PrPlaneArgs {
     const double* kzc;          // [KR][K]
@@ -60,7 +72,8 @@ template <typename T> struct PrPlaneArgs {
     int pdl;                    // launched with programmatic stream serialization (host-side flag only)
     // fused finalize (FUSE variants: every CTA of the grid is resident; see pr_fused_finalize)
     unsigned* arrive;           // grid-arrival counter, monotonic over the iterations of a run (zeroed by pr_run)
-    PrFinalArgs fin;
+    PrFinalArgs fin;            // iter / cur / last_iter describe the FIRST iteration of this launch
+    int niter;                  // iterations this launch runs back to back (FUSE: a second grid barrier separates them)
     const unsigned char* mask;
     cplx<T>* pupil0; cplx<T>* pupil1;
     double* diffpart;           // [2][gridDim.x][2]
@@ -93,7 +106,7 @@ __device__ __forceinline__ cplx<float> replace_magnitude(cplx<float> a, float I,
 
 // NTH = 256 (two CTAs per SM) or 512 (one wide CTA per SM: short stacks, where there are fewer plane
 // quarters than SMs and latency hiding has to come from inside the CTA).
-template <typename T, int NT> __device__ void pr_fused_finalize(const PrPlaneArgs<T>& a, double* red);
+template <typename T, int NT> __device__ int pr_fused_finalize(const PrPlaneArgs<T>& a, int it, double* red);
 
 template <typename T, int N, int M, bool TAB, int NTH, bool FUSE = false>
 __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) pr_plane_kernel(PrPlaneArgs<T> a) {
@@ -118,7 +131,7 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
     if constexpr (TAB) stage_dtab<T, NT>(Dq, dsrc, dtab_size(a.f0), tid);
     const int K = a.K, KP = a.KP, f0 = a.f0;
     const double z = a.z[plane];
-    const cplx<T>* __restrict__ pupil = a.pupilc;
+    const cplx<T>* pupil = a.pupilc;
     const double* __restrict__ kzc = a.kzc;
 
     for (int i = tid; i < N; i += NT) tws[i] = a.tw[i];
@@ -142,6 +155,11 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
     PR_MARK(1);
     if (a.state->stopped) return;
     __syncthreads();
+    // FUSE: the launch runs a.niter iterations; the in-kernel finalize ends each one behind a grid-wide barrier and a
+    // second barrier publishes the new pupil.  tws and the staged defocus table survive an iteration (the forward
+    // column phase restages the table once EX is free; the finalize's scratch lies in U).
+    for (int it = 0;; ++it) {
+    if constexpr (FUSE) { if (it) pupil = ((a.fin.cur + it) & 1) ? a.pupil1 : a.pupil0; }
     // ---------------- inverse: fold + columns ----------------
     {
         constexpr int Q1 = CP::R1, L1 = CP::R2;
@@ -299,7 +317,12 @@ __global__ void __launch_bounds__(NTH, (sizeof(T) == 4 && NTH == 256) ? 2 : 1) p
         a.mse_part[blockIdx.x] = s;
     }
     PR_MARK(5);
-    if constexpr (FUSE) pr_fused_finalize<T, NT>(a, reinterpret_cast<double*>(smem_raw));
+    if constexpr (FUSE) {
+        if (pr_fused_finalize<T, NT>(a, it, reinterpret_cast<double*>(U)) || it + 1 >= a.niter) break;
+    } else {
+        break;
+    }
+    }
     PR_MARK(9);
 }
 
@@ -392,17 +415,36 @@ constexpr int PR_FIN_LANES = 8;     // threads sharing one pixel's sum over the 
 // same summation order as pr_finalize_kernel (8 lanes per pixel, lane l adds the parts l, l + 8, ... in order, then the
 // lanes are added in order), so both paths produce bit-identical pupils.  The scalars (mse, mse_diff, pupil_diff, the
 // stop decision) are evaluated redundantly and identically by every CTA.  One kernel per iteration.
-template <typename T, int NT> __device__ void pr_fused_finalize(const PrPlaneArgs<T>& a, double* smem_d) {
+template <typename T, int NT> __device__ int pr_fused_finalize(const PrPlaneArgs<T>& a, int it, double* smem_d) {
     const int tid = threadIdx.x, nblk = gridDim.x;
     const PrFinalArgs& f = a.fin;
+    const int iter = f.iter + it, cur = (f.cur + it) & 1;             // this iteration of the launch
+    const bool last_iter = f.last_iter && it + 1 == a.niter;
     __shared__ int s_stop;
-    const double old_mse = (tid == 0 && f.iter > 0) ? a.mse[f.iter - 1] : 0.0;      // written by the previous launch
+    // A thread owns VL of a pixel's PR_FIN_LANES part-lanes (lane and lane + TL) and keeps one sum per part-lane, so the
+    // summation order is pr_finalize_kernel's while NT / TL pixels -- this CTA's whole share on the fixture -- are
+    // reduced in ONE pass: every load of the tail shares a single L2 round trip.
+    constexpr int VL = 2, TL = PR_FIN_LANES / VL, PIX = NT / TL, NPB = 16;      // NPB: parts per part-lane and batch
+    const int KK = f.K * f.K;
+    const int per = (KK + nblk - 1) / nblk, p0 = blockIdx.x * per, p1 = min(KK, p0 + per);
+    const int px = tid % PIX, lane = tid / PIX;
+    const cplx<T>* __restrict__ oldp = cur ? a.pupil1 : a.pupil0;
+    cplx<T>* __restrict__ newp = cur ? a.pupil0 : a.pupil1;
+    double2* red2 = reinterpret_cast<double2*>(smem_d);                 // [PR_FIN_LANES][PIX]
+    double* redn = smem_d + 2 * PR_FIN_LANES * PIX;                     // [NT / 32][2]
+    double* scal = redn + 2 * (NT / 32);                                // squared-error sum, pupil-difference numerator / denominator
+    // ---- what does not depend on the other CTAs is loaded ahead of the barrier: last iteration's mse (the thread that
+    //      takes the stop decision), the mask and the old pupil of this thread's first pixel -------------------------
+    const bool decider = tid == NT - 1;                                 // owns no pixel unless per >= PIX
+    const double old_mse = (decider && iter > 0) ? a.mse[iter - 1] : 0.0;      // written by the previous iteration
+    bool live = p0 + px < p1 && a.mask[p0 + px];                        // pixels outside the pupil are zero whatever the sum
+    const cplx<T> old0 = (lane == 0 && p0 + px < p1) ? oldp[p0 + px] : mk<T>(0, 0);
     // ---- grid barrier: this CTA's partial pupil and squared-error sum are visible before it arrives -------------
     __threadfence();
     __syncthreads();
     if (tid == 0) {
         atomicAdd(a.arrive, 1u);
-        const unsigned target = (unsigned)(f.iter + 1) * (unsigned)nblk;
+        const unsigned target = (unsigned)(2 * iter + 1) * (unsigned)nblk;    // two barriers per iteration
         unsigned seen;
         unsigned long long t0 = 0;
         s_stop = 0;
@@ -412,115 +454,111 @@ template <typename T, int NT> __device__ void pr_fused_finalize(const PrPlaneArg
             if ((spin & 1023u) == 1023u) {                      // bounded: a CTA of this grid never became resident
                 unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                 if (t0 == 0) t0 = t1;
-                else if (t1 - t0 > 2000000000ull) { s_stop = 2; a.state_rw->stopped = 3; break; }
+                else if (t1 - t0 > 2000000000ull) { s_stop = 2; a.state_rw->stopped = 3; pr_publish_progress(f.host_prog, iter, 3); break; }
             }
         }
     }
     __syncthreads();
     PR_MARK(6);
-    if (s_stop == 2) return;
-    const int KK = f.K * f.K;
-    constexpr int PIX = NT / PR_FIN_LANES;                              // pixels per pass
-    const int per = (KK + nblk - 1) / nblk, p0 = blockIdx.x * per, p1 = min(KK, p0 + per);
-    const int px = tid % PIX, lane = tid / PIX;
-    double2* red2 = reinterpret_cast<double2*>(smem_d);                 // [PR_FIN_LANES][PIX]
-    double* redn = smem_d + 2 * NT;                                     // [NT / 32][2]
-    double* scal = redn + 2 * (NT / 32);                                // squared-error sum, pupil-difference numerator / denominator
-    // ---- every load of the first pass is issued before anything waits: the partial pupils of this CTA's pixels (all
-    //      threads) and the three scalar sums (warps 0 .. 2, one each) share one L2 round trip -----------------------
+    if (s_stop == 2) return 2;
+    // ---- every load is issued before anything waits: the partial pupils of this CTA's pixels (all threads) and the
+    //      three scalar sums (warps 0 .. 2, one each) --------------------------------------------------------------
     if (tid < 96) {
         const int w = tid >> 5, l = tid & 31;
-        const double* src = w == 0 ? a.mse_part : a.diffpart + (size_t)(f.iter & 1) * 2 * nblk + (w - 1);
+        const double* src = w == 0 ? a.mse_part : a.diffpart + (size_t)(iter & 1) * 2 * nblk + (w - 1);
         const int n = w == 0 ? f.nmse : nblk, stride = w == 0 ? 1 : 2;
         double sv = 0.0;
-        if (w == 0 || f.iter > 0) sv = warp_sum_fixed(src, n, stride, l);
+        if (w == 0 || iter > 0) sv = warp_sum_fixed(src, n, stride, l);
         if (l == 0) scal[w] = sv;
     }
-    constexpr int NPB = 16;                                             // parts per lane and batch
-    cplx<T> v[NPB];
-    {
-        const int p = p0 + px;
-        const bool live = p < p1 && a.mask[p];                          // pixels outside the pupil are zero whatever the sum
+    cplx<T> v[VL][NPB];
+    auto load_batch = [&](int p, bool lv) {
         const cplx<T>* __restrict__ pp = a.partial + p;
 #pragma unroll
-        for (int k = 0; k < NPB; ++k) {
-            const int q = lane + k * PR_FIN_LANES;
-            v[k] = (live && q < f.nparts) ? pp[(size_t)q * KK] : mk<T>(0, 0);
-        }
-    }
+        for (int j = 0; j < VL; ++j)
+#pragma unroll
+            for (int k = 0; k < NPB; ++k) {
+                const int q = lane + j * TL + k * PR_FIN_LANES;
+                v[j][k] = (lv && q < f.nparts) ? pp[(size_t)q * KK] : mk<T>(0, 0);
+            }
+    };
+    load_batch(p0 + px, live);
     __syncthreads();
-    if (tid == 0) {
+    if (decider) {                                                      // the other threads go on to their sums
         const double new_mse = scal[0] / f.npix_total;
         double md = nan(""), pd = nan("");
-        if (f.iter > 0) {
+        if (iter > 0) {
             md = fabs(old_mse - new_mse) / old_mse;                    // phaseretrieval.py:103
             pd = scal[1] / scal[2];                                    // :105
         }
         const int stop = (pd < f.pupil_tol) || (md < f.mse_tol) || (new_mse < f.mse_tol);   // :114
         s_stop = stop;
         if (blockIdx.x == 0) {
-            a.mse[f.iter] = new_mse; a.mse_diff[f.iter] = md; a.pupil_diff[f.iter] = pd;
-            a.state_rw->iters_run = f.iter + 1;
+            a.mse[iter] = new_mse; a.mse_diff[iter] = md; a.pupil_diff[iter] = pd;
+            a.state_rw->iters_run = iter + 1;
             if (stop) { a.state_rw->final_is_next = 0; a.state_rw->stopped = 1; }
-            else if (f.last_iter) a.state_rw->final_is_next = 1;
+            else if (last_iter) a.state_rw->final_is_next = 1;
+            pr_publish_progress(f.host_prog, iter + 1, stop);
         }
     }
-    __syncthreads();
-    PR_MARK(7);
-    if (s_stop) return;
-    const cplx<T>* __restrict__ oldp = f.cur ? a.pupil1 : a.pupil0;
-    cplx<T>* __restrict__ newp = f.cur ? a.pupil0 : a.pupil1;
     double num = 0.0, den = 0.0;
     for (int base = p0; base < p1; base += PIX) {
         const int p = base + px;
-        double sx = 0.0, sy = 0.0;
+        double sx[VL], sy[VL];
 #pragma unroll
-        for (int k = 0; k < NPB; ++k) { sx += (double)v[k].x; sy += (double)v[k].y; }
-        if (p < p1 && a.mask[p]) {
-            const cplx<T>* __restrict__ pp = a.partial + p;
-            for (int q0 = lane + NPB * PR_FIN_LANES; q0 < f.nparts; q0 += NPB * PR_FIN_LANES) {     // more than 128 parts
-                cplx<T> u[NPB];
+        for (int j = 0; j < VL; ++j) {
+            sx[j] = 0.0; sy[j] = 0.0;
 #pragma unroll
-                for (int k = 0; k < NPB; ++k) {
-                    const int q = q0 + k * PR_FIN_LANES;
-                    u[k] = q < f.nparts ? pp[(size_t)q * KK] : mk<T>(0, 0);
-                }
-#pragma unroll
-                for (int k = 0; k < NPB; ++k) { sx += (double)u[k].x; sy += (double)u[k].y; }
-            }
+            for (int k = 0; k < NPB; ++k) { sx[j] += (double)v[j][k].x; sy[j] += (double)v[j][k].y; }
         }
-        // the next pass's first batch is in flight while this one is reduced
-        {
-            const int pn = p + PIX;
-            const bool live = pn < p1 && a.mask[pn];
-            const cplx<T>* __restrict__ pp = a.partial + pn;
+        if (live && f.nparts > NPB * PR_FIN_LANES) {                    // more than 128 parts
+            const cplx<T>* __restrict__ pp = a.partial + p;
 #pragma unroll
-            for (int k = 0; k < NPB; ++k) {
-                const int q = lane + k * PR_FIN_LANES;
-                v[k] = (live && q < f.nparts) ? pp[(size_t)q * KK] : mk<T>(0, 0);
-            }
+            for (int j = 0; j < VL; ++j)
+                for (int q0 = lane + j * TL + NPB * PR_FIN_LANES; q0 < f.nparts; q0 += NPB * PR_FIN_LANES) {
+                    cplx<T> u[NPB];
+#pragma unroll
+                    for (int k = 0; k < NPB; ++k) {
+                        const int q = q0 + k * PR_FIN_LANES;
+                        u[k] = q < f.nparts ? pp[(size_t)q * KK] : mk<T>(0, 0);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NPB; ++k) { sx[j] += (double)u[k].x; sy[j] += (double)u[k].y; }
+                }
+        }
+        // a further pass (fewer CTAs than on the fixture): its first batch is in flight while this one is reduced
+        bool live_n = false;
+        if (base + PIX < p1) {
+            live_n = p + PIX < p1 && a.mask[p + PIX];
+            load_batch(p + PIX, live_n);
         }
         if (base != p0) __syncthreads();
-        red2[lane * PIX + px] = make_double2(sx, sy);
-        __syncthreads();
-        if (lane == 0 && p < p1) {
-            sx = 0.0; sy = 0.0;
 #pragma unroll
-            for (int l = 0; l < PR_FIN_LANES; ++l) { sx += red2[l * PIX + px].x; sy += red2[l * PIX + px].y; }
-            const double m = a.mask[p] ? 1.0 : 0.0;
-            sx = sx / f.nz_total * m; sy = sy / f.nz_total * m;        // mean(0) * mask   :127
+        for (int j = 0; j < VL; ++j) red2[(lane + j * TL) * PIX + px] = make_double2(sx[j], sy[j]);
+        __syncthreads();
+        if (base == p0) {
+            PR_MARK(7);
+            if (s_stop) return 1;                                       // written before the barrier above
+        }
+        if (lane == 0 && p < p1) {
+            double tx = 0.0, ty = 0.0;
+#pragma unroll
+            for (int l = 0; l < PR_FIN_LANES; ++l) { tx += red2[l * PIX + px].x; ty += red2[l * PIX + px].y; }
+            const double m = live ? 1.0 : 0.0;
+            tx = tx / f.nz_total * m; ty = ty / f.nz_total * m;        // mean(0) * mask   :127
             if (f.phase_only) {                                        // exp(i angle(.)) * mask   :130
-                const double mag = hypot(sx, sy);
-                if (mag > 0.0) { sx = sx / mag * m; sy = sy / mag * m; }
-                else { sx = m; sy = 0.0; }
+                const double mag = hypot(tx, ty);
+                if (mag > 0.0) { tx = tx / mag * m; ty = ty / mag * m; }
+                else { tx = m; ty = 0.0; }
             }
-            const cplx<T> o = oldp[p];
-            const cplx<T> nv = mk<T>((T)sx, (T)sy);
+            const cplx<T> o = base == p0 ? old0 : oldp[p];
+            const cplx<T> nv = mk<T>((T)tx, (T)ty);
             newp[p] = nv;
             const double dx = (double)o.x - (double)nv.x, dy = (double)o.y - (double)nv.y;
             num += dx * dx + dy * dy;
             den += (double)o.x * (double)o.x + (double)o.y * (double)o.y;
         }
+        live = live_n;
     }
     PR_MARK(8);
     // deterministic block sums of num / den (fixed shuffle tree, warps added in order)
@@ -531,10 +569,35 @@ template <typename T, int NT> __device__ void pr_fused_finalize(const PrPlaneArg
     if (tid == 0) {
         double n2 = 0.0, d2 = 0.0;
         for (int w = 0; w < NT / 32; ++w) { n2 += redn[2 * w]; d2 += redn[2 * w + 1]; }
-        double* dp = a.diffpart + (size_t)((f.iter + 1) & 1) * 2 * nblk;
+        double* dp = a.diffpart + (size_t)((iter + 1) & 1) * 2 * nblk;
         dp[2 * blockIdx.x] = n2; dp[2 * blockIdx.x + 1] = d2;
     }
+    // ---- second grid barrier: the new pupil, this CTA's share of the pupil-difference sums and mse[iter] are visible
+    //      to every CTA before the next iteration of this launch reads them.  The last iteration of a launch only
+    //      arrives (the counter stays two per iteration): the kernel boundary orders the rest. ------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(a.arrive, 1u);
+        if (it + 1 < a.niter) {
+            const unsigned target = (unsigned)(2 * iter + 2) * (unsigned)nblk;
+            unsigned seen;
+            unsigned long long t0 = 0;
+            for (unsigned spin = 0;; ++spin) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.arrive) : "memory");
+                if ((int)(seen - target) >= 0) break;
+                if ((spin & 1023u) == 1023u) {
+                    unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t0 == 0) t0 = t1;
+                    else if (t1 - t0 > 2000000000ull) { s_stop = 2; a.state_rw->stopped = 3; pr_publish_progress(f.host_prog, iter, 3); break; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    return s_stop == 2 ? 2 : 0;
 }
+
 
 // TP = cplx<T> (per-CTA partials of this rank) or double2 (all-reduced sums: nparts = 1 and
 // the squared-error numerator sits at index KK).  Block = 256 threads = 32 pixels x 8 part lanes.
@@ -577,6 +640,7 @@ __global__ void __launch_bounds__(256) pr_finalize_kernel(PrFinalArgs a, const T
                 state->iters_run = a.iter + 1;
                 if (stop) { state->final_is_next = 0; state->stopped = 1; }
                 else if (a.last_iter) state->final_is_next = 1;
+                pr_publish_progress(a.host_prog, a.iter + 1, stop);
             }
         }
     }
@@ -700,7 +764,7 @@ __global__ void __launch_bounds__(256) pr_finalize_peers_kernel(PrFinalArgs a, P
             if (p < KK) { ok &= ll_load(src + 2 * p, flag, vx); ok &= ll_load(src + 2 * p + 1, flag, vy); }
             msum += m; sx += vx; sy += vy;
         }
-        if (!__all_sync(0xffffffffu, ok)) { if (tid == 0) state->stopped = 2; return; }
+        if (!__all_sync(0xffffffffu, ok)) { if (tid == 0) { state->stopped = 2; pr_publish_progress(a.host_prog, a.iter, 2); } return; }
         // ---- scalars and the stop test: identical on every CTA of every rank ----
         const double new_mse = msum / a.npix_total;
         double md = nan(""), pd = nan("");
@@ -718,6 +782,7 @@ __global__ void __launch_bounds__(256) pr_finalize_peers_kernel(PrFinalArgs a, P
             state->iters_run = a.iter + 1;
             if (stop) { state->final_is_next = 0; state->stopped = 1; }
             else if (a.last_iter) state->final_is_next = 1;
+            pr_publish_progress(a.host_prog, a.iter + 1, stop);
         }
         if (!stop) {
             const cplx<T>* __restrict__ oldp = a.cur ? pupil1 : pupil0;

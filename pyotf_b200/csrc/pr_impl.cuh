@@ -2,6 +2,7 @@
 // iteration loop of retrieve_phase (pyotf/phaseretrieval.py:95-135) as back-to-back kernel
 // launches with the convergence test on the device, and the optional z-sharded all-reduce.
 #pragma once
+#include <thread>
 #include "common.cuh"
 #include "pr.cuh"
 #include "pr_big.cuh"
@@ -93,11 +94,13 @@ template <typename T, int N> int pr_plane_launch_n(const pyotf_hanser* h, int M,
     return 1;
 }
 
-template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, bool pdl, cudaStream_t st, const PrFinalArgs* fin = nullptr) {
+template <typename T> int pr_plane_launch(const pyotf_pr* s, int cur, bool pdl, cudaStream_t st, const PrFinalArgs* fin = nullptr,
+                                          int niter = 1) {
     const pyotf_hanser* h = s->h;
     PrPlaneArgs<T> a;
     a.pdl = pdl ? 1 : 0;
     a.arrive = nullptr;
+    a.niter = niter;
     if (fin) {
         a.arrive = s->arrive; a.fin = *fin; a.mask = h->maskc; a.pupil0 = (cplx<T>*)s->pupil[0]; a.pupil1 = (cplx<T>*)s->pupil[1];
         a.diffpart = s->diffpart; a.mse = s->mse; a.mse_diff = s->mse_diff; a.pupil_diff = s->pupil_diff; a.state_rw = (PrState*)s->state;
@@ -264,13 +267,29 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
         PYOTF_CUDA_OK(cudaMallocAsync(&s->pupil_diff, sizeof(double) * max_iters, st));
         s->cap_iters = max_iters;
     }
-    constexpr int CHK = 8, NSLOT = 4;
-    if (!s->h_flags) {
-        PYOTF_CUDA_OK(cudaMallocHost(&s->h_flags, sizeof(int) * NSLOT));
-        for (int i = 0; i < NSLOT; ++i) PYOTF_CUDA_OK(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
+    constexpr int CHK = 8;
+    if (!s->h_prog) {
+        PYOTF_CUDA_OK(cudaHostAlloc(&s->h_prog, sizeof(int) * 2, cudaHostAllocMapped | cudaHostAllocPortable));
+        PYOTF_CUDA_OK(cudaHostGetDevicePointer(&s->d_prog, s->h_prog, 0));
     }
+    // (nothing of an earlier run is in flight: every run ends with a stream synchronisation)
+    volatile int* hp = s->h_prog;
+    hp[0] = 0; hp[1] = 0;
+    // true: the device has stopped.  Returns once `need` iterations have finished; the host stays at most 2 * CHK
+    // iterations ahead of the device so that little is enqueued past an early stop.
+    auto stopped_before = [&](int need) {
+        for (unsigned spins = 0;; ++spins) {
+            if (hp[0]) return true;
+            if (hp[1] >= need) return false;
+            if ((spins & 1023u) == 1023u) {
+                if (cudaStreamQuery(st) != cudaErrorNotReady) return hp[0] != 0;    // drained (or failed): nothing to wait for
+                std::this_thread::yield();
+            }
+        }
+    };
     PYOTF_CUDA_OK(cudaMemsetAsync(s->state, 0, sizeof(PrState), st));
     PrFinalArgs fa;
+    fa.host_prog = (int*)s->d_prog;
     fa.K = h->K; fa.phase_only = phase_only;
     fa.npix_total = (double)s->nz_total * h->N * h->N; fa.nz_total = (double)s->nz_total;
     fa.pupil_tol = pupil_tol; fa.mse_tol = mse_tol;
@@ -284,28 +303,27 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
     const bool use_pdl = (!comm || window) && !s->generic && !no_pdl;
     const bool fused = s->fuse && !comm && s->dtab && !dbg_skip_any();
     if (fused) PYOTF_CUDA_OK(cudaMemsetAsync(s->arrive, 0, sizeof(unsigned), st));
+    // iterations per fused launch: CHK (the poll period) unless PYOTF_B200_PR_ITERS_PER_LAUNCH says otherwise (1 = the
+    // one-launch-per-iteration loop; the tests compare the two)
+    int chunk = CHK;
+    if (const char* e = getenv("PYOTF_B200_PR_ITERS_PER_LAUNCH")) { chunk = std::max(1, std::min(CHK, atoi(e))); if (CHK % chunk) chunk = 1; }
+    s->kernel_launches = 0;
     PrPeers peers = {};
     if (window) { peers.world = s->win_world; peers.rank = s->win_rank; for (int r = 0; r < s->win_world; ++r) peers.win[r] = s->peer[r]; }
     for (int i = 0; i < max_iters; ++i) {
-        if (i % CHK == 0 && i >= 2 * CHK) {            // stay at most ~2*CHK iterations ahead of the device
-            const int slot = (i / CHK - 2) % NSLOT;
-            PYOTF_CUDA_OK(cudaEventSynchronize(s->ev[slot]));
-            if (s->h_flags[slot]) break;
-        }
+        if (i % CHK == 0 && i >= 2 * CHK && stopped_before(i - CHK)) break;   // stay at most ~2*CHK iterations ahead of the device
         const int cur = (start + i) & 1;
         static const int dbg_skip = [] { const char* e = getenv("PYOTF_B200_PR_DEBUG_SKIP"); return e ? atoi(e) : 0; }();   // timing experiments only: 1 = no plane kernel, 2 = no finalize
         int rc = 0;
         fa.iter = i; fa.cur = cur; fa.last_iter = i == max_iters - 1; fa.nmse = s->nmse;
         if (fused) {
-            fa.nparts = s->nparts;
-            rc = pr_plane_launch<T>(s, cur, use_pdl, st, &fa);
+            // one launch runs the iterations up to the next stop-flag poll (at most CHK) behind in-kernel grid barriers
+            const int n = std::min(chunk - i % chunk, max_iters - i);
+            fa.nparts = s->nparts; fa.last_iter = i + n == max_iters;
+            rc = pr_plane_launch<T>(s, cur, use_pdl, st, &fa, n);
             if (rc) return rc;
-            ++launched;
-            if (i % CHK == CHK - 1) {
-                const int slot = (i / CHK) % NSLOT;
-                PYOTF_CUDA_OK(cudaMemcpyAsync(&s->h_flags[slot], &((PrState*)s->state)->stopped, sizeof(int), cudaMemcpyDeviceToHost, st));
-                PYOTF_CUDA_OK(cudaEventRecord(s->ev[slot], st));
-            }
+            launched += n; ++s->kernel_launches;
+            i += n - 1;
             continue;
         }
         if (dbg_skip != 1) rc = s->generic ? pr_generic_passes<T>(s, cur, st) : pr_plane_launch<T>(s, cur, use_pdl, st);
@@ -351,12 +369,6 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
         }
         PYOTF_CUDA_OK(cudaGetLastError());
         ++launched;
-        if (i % CHK == CHK - 1) {
-            const int slot = (i / CHK) % NSLOT;
-            PYOTF_CUDA_OK(cudaMemcpyAsync(&s->h_flags[slot], &((PrState*)s->state)->stopped, sizeof(int),
-                                          cudaMemcpyDeviceToHost, st));
-            PYOTF_CUDA_OK(cudaEventRecord(s->ev[slot], st));
-        }
     }
     PrState hs;
     PYOTF_CUDA_OK(cudaMemcpyAsync(&hs, s->state, sizeof(PrState), cudaMemcpyDeviceToHost, st));

@@ -94,10 +94,13 @@ def psqrt(data):
 def slice_maker(centers, widths):
     """Slices of ``widths`` centred on ``centers`` (clean-room stand-in for dphtools.slice_maker).
 
-    ``widths`` may be a scalar (applied to every axis).  Starts are clipped at 0 and the window then keeps its full
-    width (``slice(0, w)``).  UNPINNED: dphtools is not vendored by the reference, so edge-clipped windows could not be
-    compared with the original (which may return a shorter window there); windows that fit are unambiguous and are
-    what the reference's own shape / centre tests exercise (tests/test_api_gpu.py).
+    ``widths`` may be a scalar (applied to every axis).  A window is ``[c - w // 2, c - w // 2 + w)``; only its START is
+    clipped at 0, so a window that hangs over the lower edge comes back shorter (the published dphtools rule as far as
+    it is known here), and one that ends at or before 0 is empty.  UNPINNED: dphtools is not vendored by the reference,
+    so edge-clipped windows could not be compared with the original; windows that fit are unambiguous and are what the
+    reference's own shape / centre tests exercise (tests/test_api_gpu.py).  In ``prep_data_for_PR`` the centre is
+    ``(n + 1) // 2``: a clipped start there implies a stop beyond the array, so either clipping rule crops the same
+    elements (tests/test_utils_cpu.py).
     """
     centers = np.atleast_1d(centers)
     widths = np.broadcast_to(np.atleast_1d(widths), centers.shape)
@@ -107,8 +110,10 @@ def slice_maker(centers, widths):
         if w < 0:
             raise ValueError("width must be non-negative")
         lo = int(round(float(c))) - w // 2
-        lo = max(lo, 0)
-        out.append(slice(lo, lo + w))
+        hi = lo + w
+        if hi <= 0:
+            lo, hi = 0, 0
+        out.append(slice(max(lo, 0), hi))
     return tuple(out)
 
 

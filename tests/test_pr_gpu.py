@@ -332,13 +332,16 @@ def test_one_kernel_per_iteration_equals_two_kernel_loop(precision, nz, phase_on
     rt = torch.float32 if precision == "fp32" else torch.float64
     dev = torch.as_tensor(data, device="cuda").to(rt)
     out = {}
-    for label in ("fused", "two"):
+    for label in ("fused", "fused1", "two"):
+        # "fused": up to 8 iterations per launch behind in-kernel grid barriers; "fused1": one launch per iteration
+        monkeypatch.delenv("PYOTF_B200_PR_NO_FUSE", raising=False)
+        monkeypatch.delenv("PYOTF_B200_PR_ITERS_PER_LAUNCH", raising=False)
         if label == "two":
             monkeypatch.setenv("PYOTF_B200_PR_NO_FUSE", "1")
-        else:
-            monkeypatch.delenv("PYOTF_B200_PR_NO_FUSE", raising=False)
+        elif label == "fused1":
+            monkeypatch.setenv("PYOTF_B200_PR_ITERS_PER_LAUNCH", "1")
         st = eng.PRState(OPT["wl"], OPT["na"], OPT["ni"], OPT["res"], 256, z, dev, precision)
-        assert st.kernels_per_iteration() == (1 if label == "fused" and precision == "fp32" else 2)
+        assert st.kernels_per_iteration() == (1 if label != "two" and precision == "fp32" else 2)
         mse, mse_diff, pupil_diff = st.run(30, 0.0, mtol, phase_only=phase_only)
         out[label] = (np.array(mse), np.array(mse_diff), np.array(pupil_diff), st.get_pupil(0).cpu().numpy(), st.get_pupil(1).cpu().numpy())
         # a second run on the same state (PhaseRetrieval.step): the arrival counter restarts
@@ -352,3 +355,5 @@ def test_one_kernel_per_iteration_equals_two_kernel_loop(precision, nz, phase_on
             np.testing.assert_allclose(x[1:], y[1:], rtol=1e-12, atol=0)
         else:
             np.testing.assert_array_equal(x, y)
+    for x, y in zip(out["fused"], out["fused1"]):      # the same kernel, 8 or 1 iterations per launch: everything identical
+        np.testing.assert_array_equal(x, y)
