@@ -229,6 +229,9 @@ def bench_pr(precision, rank, world, dist, reps=5, iters=100, extras=True):
            "workload": "retrieve_phase on the 25 x 256^2 fixture stack, 100 iterations, tol 0 (BASELINE config 2)",
            "rows_per_cta": st.rows_per_cta, "ctas_per_iteration": st.nparts,
            "kernels_per_iteration": st.kernels_per_iteration(world > 1), "final_mse": float(mse[-1]),
+           # the fused single-GPU loop runs up to 8 iterations per launch behind in-kernel grid barriers
+           "iterations_per_launch": (int(os.environ.get("PYOTF_B200_PR_ITERS_PER_LAUNCH", 8))
+                                     if st.kernels_per_iteration(world > 1) == 1 else 1),
            "parallelism": f"z-shard x{world}" + ("" if world == 1 else " + per-iteration sum over ranks inside the finalize "
                                                                       "kernel (peer windows over NVLink, no NCCL call)")}
     # roofline of one iteration: nz*N^2*s_r of measured data + 2 compact... full-grid pupils (in/out)

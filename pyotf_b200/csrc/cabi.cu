@@ -436,7 +436,11 @@ int pyotf_b200_pr_destroy(pyotf_pr_t* s) {
     void* bufs[] = {s->z, s->data, s->pupil[0], s->pupil[1], s->partial, s->mse_part, s->sums, s->diffpart, s->mse,
                     s->mse_diff, s->pupil_diff, s->state, s->dtab, s->W, s->P, s->arrive};
     for (void* b : bufs) if (b) cudaFreeAsync(b, st);         // stream-ordered: returns to the cached pool
-    if (s->h_prog) cudaFreeHost(s->h_prog);
+    if (s->h_prog) {
+        // the words may still be written by kernels of a run that failed half-way: drain before the slot is reused
+        if (s->prog_slot >= 0) { if (s->in_flight) cudaStreamSynchronize(st); pyotf::ProgressSlots::get().release(s->prog_slot); }
+        else cudaFreeHost(s->h_prog);
+    }
     pyotf_b200_hanser_destroy(s->h);
     delete s;
     return 0;

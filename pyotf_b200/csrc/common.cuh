@@ -1,5 +1,7 @@
 // Shared host-side helpers for the C ABI: error reporting and handle definitions.
 #pragma once
+#include <vector>
+#include <mutex>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <string>
@@ -48,6 +50,32 @@ inline int current_device_slot() {
     cudaGetDevice(&dev);
     return dev >= 0 && dev < PYOTF_MAX_DEVICES ? dev : 0;
 }
+
+// Pinned, device-mapped progress words of the phase-retrieval loops (two ints per slot: stopped, iterations finished).
+// cudaHostAlloc / cudaFreeHost cost a fraction of a millisecond each and synchronise the device, so the slots come out
+// of one page that lives as long as the process; a state borrows a slot for its lifetime.
+struct ProgressSlots {
+    static constexpr int NSLOT = 512;
+    std::mutex mu;
+    int* host = nullptr;
+    void* dev = nullptr;
+    std::vector<int> free_list;
+    static ProgressSlots& get() { static ProgressSlots* p = new ProgressSlots; return *p; }   // never destroyed (no CUDA calls at exit)
+    // returns a slot index, or -1 (out of slots / allocation failed: the caller allocates its own words)
+    int acquire(int** h, void** d) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!host) {
+            if (cudaHostAlloc(&host, sizeof(int) * 2 * NSLOT, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+                cudaHostGetDevicePointer(&dev, host, 0) != cudaSuccess) { cudaGetLastError(); host = nullptr; return -1; }
+            for (int i = NSLOT - 1; i >= 0; --i) free_list.push_back(i);
+        }
+        if (free_list.empty()) return -1;
+        const int i = free_list.back(); free_list.pop_back();
+        *h = host + 2 * i; *d = (char*)dev + sizeof(int) * 2 * i;
+        return i;
+    }
+    void release(int i) { std::lock_guard<std::mutex> lk(mu); free_list.push_back(i); }
+};
 
 constexpr int PYOTF_PAD_ROWS = 64;   // >= the largest rows-per-CTA M of K1
 inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -108,6 +136,8 @@ struct pyotf_pr {
     long long epoch_base = 0;       // epochs are monotonic over the life of the window
     int* h_prog = nullptr;          // pinned, mapped: [0] stopped, [1] iterations finished (written by the kernels)
     void* d_prog = nullptr;         // its device address
+    int prog_slot = -1;             // >= 0: borrowed from pyotf::ProgressSlots; -1: own allocation
+    int in_flight = 0;              // a run was enqueued and has not been seen to finish (it failed half-way)
 };
 
 namespace pyotf {

@@ -1,5 +1,6 @@
 // Per-dtype host launchers for K1 (instantiated in hanser_f32.cu / hanser_f64.cu).
 #pragma once
+#include <cstring>
 #include <algorithm>
 #include <cstdlib>
 
@@ -454,6 +455,62 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
         }
     }
     return hanser_launch_big<T>(h, z, nz, pupilc, batch, pupil_stride, psfa, psfi, smem_limit, s);
+}
+
+// K1 on caller-built per-plane quadrant tables, no handle: plane p of the stack is fftshift(ifft2(P_p)) with
+// P_p(fy, fx) = tables[p][|fy| * dtab_pitch(f0) + |fx|] for |fy|, |fx| <= -f0 (a pupil even in ky and in kx -- what
+// `pupil * amp * defocus` is for the ideal pupil of the scalar HanserPSF model, and what the z transform of the scalar
+// SheppardPSF cap is at every z, sheppard_impl.cuh).  Runs the even-symmetric variant of the fused kernel (half the
+// columns, half the rows).  psfa [nz][N][N] and / or psfi = |psfa|^2.  Returns 3 when the support box does not fit the
+// fused on-chip kernel (the caller falls back).
+template <typename T> __global__ void hanser_zero_z_kernel(double* __restrict__ z, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = 0.0;
+}
+
+template <typename T>
+int hanser_launch_tables(int N, int f0, const void* tables, int nz, void* psfa, void* psfi, cudaStream_t s) {
+    if (!(N == 32 || N == 64 || N == 128 || N == 256) || f0 >= 0 || -f0 >= N / 2 || nz < 1 || nz > 16383) return 3;
+    pyotf_hanser hd;                                   // the launch layers read the geometry and the device only
+    PYOTF_CUDA_OK(cudaGetDevice(&hd.device));
+    hd.N = N; hd.f0 = f0; hd.K = 1 - 2 * f0;
+    hd.KP = hd.K + ((8 - hd.K % 16) + 16) % 16;
+    hd.KR = hd.K + PYOTF_PAD_ROWS; hd.nvec = 1;
+    const int ntab = hanser_ntab<T>(&hd);
+    int smem_limit = 0;
+    PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, hd.device));
+    size_t need = (size_t)-1;
+    switch (N) {                                       // (launch_n sizes its choice on the full pitch)
+        case 32:  need = hanser_smem_for<T, 32>(32, hd.KP); break;
+        case 64:  need = hanser_smem_for<T, 64>(32, hd.KP); break;
+        case 128: need = hanser_smem_for<T, 128>(32, hd.KP); break;
+        default:  need = hanser_smem_for<T, 256>(32, hd.KP); break;
+    }
+    if (!ntab || need > (size_t)smem_limit) return 3;
+    keep_scratch_pool();
+    char* tmp = nullptr;
+    const size_t tw_bytes = sizeof(cplx<T>) * (size_t)N;
+    PYOTF_CUDA_OK(cudaMallocAsync(&tmp, tw_bytes + sizeof(double) * (size_t)nz, s));
+    cplx<T>* tw = (cplx<T>*)tmp;
+    double* z = (double*)(tmp + tw_bytes);
+    twiddle_kernel<T><<<(N + 255) / 256, 256, 0, s>>>(N, tw);
+    hanser_zero_z_kernel<T><<<(nz + 255) / 256, 256, 0, s>>>(z, nz);      // the tables are final: no plane position enters
+    PYOTF_CUDA_OK(cudaGetLastError());
+    HanserArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.tw = tw; a.dtab = (const cplx<T>*)tables; a.z = z;
+    a.amp_in_tab = 1;                                  // nothing multiplies the table: the even-symmetric variant runs
+    a.psfi = (T*)psfi; a.psfa = (cplx<T>*)psfa;
+    a.K = hd.K; a.KR = hd.KR; a.KP = hd.KP; a.f0 = f0; a.nz = nz; a.nvec = 1;
+    int rc;
+    switch (N) {
+        case 32:  rc = hanser_launch_n<T, 32>(&hd, a, 1, 1, smem_limit, s); break;
+        case 64:  rc = hanser_launch_n<T, 64>(&hd, a, 1, 1, smem_limit, s); break;
+        case 128: rc = hanser_launch_n<T, 128>(&hd, a, 1, 1, smem_limit, s); break;
+        default:  rc = hanser_launch_n<T, 256>(&hd, a, 1, 1, smem_limit, s); break;
+    }
+    cudaFreeAsync(tmp, s);
+    return rc;
 }
 
 }  // namespace pyotf

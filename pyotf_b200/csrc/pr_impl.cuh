@@ -269,12 +269,16 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
     }
     constexpr int CHK = 8;
     if (!s->h_prog) {
-        PYOTF_CUDA_OK(cudaHostAlloc(&s->h_prog, sizeof(int) * 2, cudaHostAllocMapped | cudaHostAllocPortable));
-        PYOTF_CUDA_OK(cudaHostGetDevicePointer(&s->d_prog, s->h_prog, 0));
+        s->prog_slot = ProgressSlots::get().acquire(&s->h_prog, &s->d_prog);
+        if (s->prog_slot < 0) {
+            PYOTF_CUDA_OK(cudaHostAlloc(&s->h_prog, sizeof(int) * 2, cudaHostAllocMapped | cudaHostAllocPortable));
+            PYOTF_CUDA_OK(cudaHostGetDevicePointer(&s->d_prog, s->h_prog, 0));
+        }
     }
     // (nothing of an earlier run is in flight: every run ends with a stream synchronisation)
     volatile int* hp = s->h_prog;
     hp[0] = 0; hp[1] = 0;
+    s->in_flight = 1;
     // true: the device has stopped.  Returns once `need` iterations have finished; the host stays at most 2 * CHK
     // iterations ahead of the device so that little is enqueued past an early stop.
     auto stopped_before = [&](int need) {
@@ -373,6 +377,7 @@ int pr_run(pyotf_pr* s, int max_iters, double pupil_tol, double mse_tol, int pha
     PrState hs;
     PYOTF_CUDA_OK(cudaMemcpyAsync(&hs, s->state, sizeof(PrState), cudaMemcpyDeviceToHost, st));
     PYOTF_CUDA_OK(cudaStreamSynchronize(st));
+    s->in_flight = 0;
     const int n = hs.iters_run;
     if (window) s->epoch_base += max_iters;            // the same on every rank, whatever was enqueued after a stop
     PYOTF_REQUIRE(hs.stopped != 2, "pr_run: a peer rank did not publish its partial sums in time (z-sharded run)");

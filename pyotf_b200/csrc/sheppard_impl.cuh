@@ -57,6 +57,26 @@ __device__ __forceinline__ T sheppard_value(const SheppardParams& p, int v, doub
     return (T)(val * a);
 }
 
+// value of the amplitude OTF at frequency (kz, ky, kx), r2zy = kz^2 + ky^2: the fp64 predicates of otf.py:503-532 in the
+// reference's operation order (the same as sheppard_otf_kernel), 0 off the shell
+template <typename T>
+__device__ __forceinline__ T sheppard_shell_value(const SheppardParams& p, int v, double kz, double ky, double kx, double r2zy) {
+    const double kr2 = __dadd_rn(r2zy, __dmul_rn(kx, kx));         // ((kz^2 + ky^2) + kx^2): numpy's order
+    if (kr2 < p.r2_lo || kr2 > p.r2_hi) return (T)0;
+    const double kr = sqrt(kr2);
+    double dkr;
+    if (p.same_dk) dkr = p.dk;
+    else if (kr2 == 0.0) dkr = 0.0;
+    else {
+        const double aa = __dmul_rn(kz, p.dkz), bb = __dmul_rn(ky, p.dk), cc = __dmul_rn(kx, p.dk);
+        dkr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(aa, aa), __dmul_rn(bb, bb)), __dmul_rn(cc, cc))) / kr;
+    }
+    const double kzz = p.dual ? fabs(kz) : kz;
+    const bool valid = (fabs(__dsub_rn(kr, p.kmag)) < dkr) && (kzz > __dadd_rn(p.kz_min, dkr));
+    if (!valid) return (T)0;
+    return sheppard_value<T>(p, v, kz, ky, kx);
+}
+
 // planeflag[zm][x] = 1 iff the plane with memory index zm (fftshift-ed layout) can hold shell voxels:
 // kzz > kz_min (valid needs kzz > kz_min + dkr, dkr >= 0) and |kz| <= kmag + max(dk, dkz) (since |kz| <= kr)
 static __global__ void sheppard_planeflag_kernel(SheppardParams p, unsigned char* __restrict__ flag) {
@@ -101,20 +121,7 @@ template <typename T> struct ShepRow : NoAcc {
         int xm = l + a.in_x; if (xm >= p.N) xm -= p.N;             // x_in[l] = OTFa[(l + in_shift) mod n]
         int xu = xm - p.N / 2; if (xu < 0) xu += p.N;
         const double kx = fftfreq_at(xu, p.N, p.kstep);
-        const double kr2 = __dadd_rn(d.r2zy, __dmul_rn(kx, kx));   // ((kz^2 + ky^2) + kx^2): numpy's order
-        if (kr2 < p.r2_lo || kr2 > p.r2_hi) return mk<T>(0, 0);
-        const double kr = sqrt(kr2);
-        double dkr;
-        if (p.same_dk) dkr = p.dk;
-        else if (kr2 == 0.0) dkr = 0.0;
-        else {
-            const double aa = __dmul_rn(d.kz, p.dkz), bb = __dmul_rn(d.ky, p.dk), cc = __dmul_rn(kx, p.dk);
-            dkr = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(aa, aa), __dmul_rn(bb, bb)), __dmul_rn(cc, cc))) / kr;
-        }
-        const double kzz = p.dual ? fabs(d.kz) : d.kz;
-        const bool valid = (fabs(__dsub_rn(kr, p.kmag)) < dkr) && (kzz > __dadd_rn(p.kz_min, dkr));
-        if (!valid) return mk<T>(0, 0);
-        return mk<T>(sheppard_value<T>(p, a.v, d.kz, d.ky, kx), 0);
+        return mk<T>(sheppard_shell_value<T>(p, a.v, d.kz, d.ky, kx, d.r2zy), 0);
     }
     __device__ __forceinline__ void store(const Line& d, int o, cplx<T> v, int&) const {
         int xm = o + a.out_x; if (xm >= a.p.N) xm -= a.p.N;
@@ -163,6 +170,156 @@ template <typename T, bool FAST = false> struct ShepCol : NoAcc {
     }
 };
 
+// ---- z-first evaluation (scalar model, power-of-two sizes) -----------------------------------------------------
+// ifftn(OTFa) = [ifft2 over (ky, kx)] o [ifft over kz].  Along kz a (ky, kx) column of the cap holds a handful of
+// voxels (the cap is one or two voxels thick; more only near its rim), so the z transform is a direct sum over them;
+// at fixed z the result is non-zero inside the disk kxy < kxy_max only; and the scalar cap is even in ky and in kx
+// (its predicates see ky^2 and kx^2 only -- exactly, in floating point too).  That is precisely the input of the
+// even-symmetric HanserPSF kernel K1: a per-plane quadrant table P_z(|fy|, |fx|) (for HanserPSF: amp * defocus).
+// sheppard_zplanes_kernel writes the tables ([zm][dtab_size], 8.5 MB at config 3) and K1 (hanser_launch_tables)
+// turns every plane into PSFa / PSFi on chip: the 134 MB volume is never formed, the only large traffic is the output.
+//
+// CTA = (16 columns ax0 .. ax0 + 15 of quadrant row ay).  Phase A: the shell voxels of each column as a list (freq
+// index, value), the predicates evaluated on the occupied kz planes only.  Phase B: lanes = 32 consecutive z, direct
+// sum over the column's list into a shared tile [z][col].  Phase C: the tile goes out row by row.
+template <typename T> struct ShepZArgs {
+    SheppardParams p;
+    int H, HP, ntab;            // support box |f| <= H; table pitch and size (dtab_pitch / dtab_size of f0 = -H)
+    int band0[2], bandn[2];     // the occupied kz planes as runs of the fftshift-ed index zm
+    cplx<T>* tab;               // [NZ][ntab]
+    double scale;               // 1 / NZ
+};
+
+constexpr int SHEPZ_COLS = 16, SHEPZ_ZC = 256, SHEPZ_TP = SHEPZ_COLS + 1;
+
+template <typename T>
+__global__ void __launch_bounds__(256) sheppard_zplanes_kernel(ShepZArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char shepz_smem[];
+    const SheppardParams& p = a.p;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int CPW = SHEPZ_COLS / 8;                                     // columns per warp
+    const int NZ = p.NZ, ZC = NZ < SHEPZ_ZC ? NZ : SHEPZ_ZC;
+    const int nband = a.bandn[0] + a.bandn[1];
+    const int ay = blockIdx.y, ax0 = blockIdx.x * SHEPZ_COLS;
+    cplx<T>* tile = reinterpret_cast<cplx<T>*>(shepz_smem);                 // [ZC][SHEPZ_TP]
+    cplx<T>* tw = tile + (size_t)ZC * SHEPZ_TP;                             // [NZ] e^{+2 pi i k / NZ}
+    T* lval = reinterpret_cast<T*>(tw + NZ);                                // [SHEPZ_COLS][nband]
+    int* lidx = reinterpret_cast<int*>(lval + (size_t)SHEPZ_COLS * nband);  // [SHEPZ_COLS][nband]
+    __shared__ int nnz[SHEPZ_COLS];
+    for (int k = tid; k < NZ; k += 256) {
+        double sn, cs;
+        sincospi(2.0 * (double)k / (double)NZ, &sn, &cs);
+        tw[k] = mk<T>((T)cs, (T)sn);
+    }
+    // ---- phase A: column lists ----
+    const double ky = __dmul_rn((double)ay, p.kstep);
+    for (int c = warp * CPW; c < warp * CPW + CPW; ++c) {
+        const int ax = ax0 + c;
+        const double kx = __dmul_rn((double)ax, p.kstep);
+        int count = 0;
+        if (ax <= a.H) {                                                    // (the pitch's padding column stays zero)
+            for (int b0 = 0; b0 < nband; b0 += 32) {
+                const int b = b0 + lane;
+                T val = (T)0;
+                int zu = 0;
+                if (b < nband) {
+                    const int zm = b < a.bandn[0] ? a.band0[0] + b : a.band0[1] + (b - a.bandn[0]);
+                    zu = zm - NZ / 2; if (zu < 0) zu += NZ;                 // unshifted frequency index
+                    const double kz = fftfreq_at(zu, NZ, p.kzstep);
+                    const double r2zy = __dadd_rn(__dmul_rn(kz, kz), __dmul_rn(ky, ky));
+                    val = sheppard_shell_value<T>(p, 0, kz, ky, kx, r2zy);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, val != (T)0);
+                if (val != (T)0) {
+                    const int pos = count + __popc(m & ((1u << lane) - 1u));
+                    lval[c * nband + pos] = val; lidx[c * nband + pos] = zu;
+                }
+                count += __popc(m);
+            }
+        }
+        if (lane == 0) nnz[c] = count;
+    }
+    __syncthreads();
+    const T scale = (T)a.scale;
+    for (int zb = 0; zb < NZ; zb += ZC) {
+        // ---- phase B: direct z transform of the warp's columns, lanes = consecutive z ----
+        for (int c = warp * CPW; c < warp * CPW + CPW; ++c) {
+            const int n = nnz[c];
+            const T* __restrict__ lv = lval + c * nband;
+            const int* __restrict__ li = lidx + c * nband;
+            for (int zg = 0; zg < ZC; zg += 32) {
+                const int z = zb + zg + lane;
+                T sx = 0, sy = 0;
+                for (int e = 0; e < n; ++e) {
+                    const cplx<T> t = tw[(li[e] * z) & (NZ - 1)];
+                    sx += lv[e] * t.x; sy += lv[e] * t.y;
+                }
+                tile[(zg + lane) * SHEPZ_TP + c] = mk<T>(sx * scale, sy * scale);
+            }
+        }
+        __syncthreads();
+        // ---- phase C: rows of the tile -> table of plane zm = (z + NZ / 2) mod NZ (fftshift along z) ----
+        {
+            const int c = lane & (SHEPZ_COLS - 1), half = lane / SHEPZ_COLS;         // two z rows per warp pass
+            if (ax0 + c < a.HP) {
+                for (int zz = warp * 2 + half; zz < ZC; zz += 16) {
+                    const int zm = (zb + zz + NZ / 2) & (NZ - 1);
+                    a.tab[(size_t)zm * a.ntab + ay * a.HP + ax0 + c] = tile[zz * SHEPZ_TP + c];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T> int hanser_launch_tables(int N, int f0, const void* tables, int nz, void* psfa, void* psfi, cudaStream_t s);
+extern template int hanser_launch_tables<float>(int, int, const void*, int, void*, void*, cudaStream_t);
+extern template int hanser_launch_tables<double>(int, int, const void*, int, void*, void*, cudaStream_t);
+
+// returns 0 (done), 3 (configuration outside this path: the caller runs the three-pass evaluation) or an error
+template <typename T>
+int sheppard_zfirst(const SheppardParams& p, const int band0[2], const int bandn[2], void* psfa_out, void* psfi_out,
+                    cudaStream_t s) {
+    const bool off = getenv("PYOTF_B200_SHEPPARD_3PASS") != nullptr;   // A/B knob, read at every call (tests compare the two)
+    const int N = p.N, NZ = p.NZ;
+    if (off || p.vec_mode != 0 || p.nvec != 1 || !(N == 32 || N == 64 || N == 128 || N == 256) || !is_pow2(NZ) || NZ < 32 ||
+        p.dk <= 0 || p.dkz <= 0 || bandn[0] < 0 || bandn[0] + bandn[1] < 1)
+        return 3;
+    // lateral extent of the cap: kr < kmag + dkr and kz > kz_min + dkr with dkr <= max(dk, dkz) give
+    // kxy^2 = kr^2 - kz^2 < kmag^2 - kz_min^2 + 2 dmax (kmag - kz_min)
+    const double dmax = std::fmax(p.dk, p.dkz);
+    const double kxy2 = p.kmag * p.kmag - p.kz_min * p.kz_min + 2.0 * dmax * (p.kmag - p.kz_min);
+    const int H = (int)std::floor(std::sqrt(kxy2) / p.kstep * (1.0 + 1e-9));
+    if (H < 1 || H >= N / 2) return 3;
+    ShepZArgs<T> a;
+    a.p = p; a.H = H; a.HP = dtab_pitch(-H); a.ntab = dtab_size(-H);
+    a.band0[0] = band0[0]; a.band0[1] = band0[1]; a.bandn[0] = bandn[0]; a.bandn[1] = bandn[1];
+    a.scale = 1.0 / (double)NZ;
+    const int nband = bandn[0] + bandn[1], ZC = NZ < SHEPZ_ZC ? NZ : SHEPZ_ZC;
+    const size_t smem = sizeof(cplx<T>) * ((size_t)ZC * SHEPZ_TP + NZ) + (sizeof(T) + sizeof(int)) * (size_t)SHEPZ_COLS * nband;
+    int dev = 0, smem_limit = 0;
+    PYOTF_CUDA_OK(cudaGetDevice(&dev));
+    PYOTF_CUDA_OK(cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)smem_limit) return 3;
+    auto kern = sheppard_zplanes_kernel<T>;
+    static thread_local size_t configured[PYOTF_MAX_DEVICES] = {};
+    const int dev_slot = current_device_slot();
+    if (smem > configured[dev_slot]) {
+        PYOTF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev_slot] = smem;
+    }
+    keep_scratch_pool();
+    PYOTF_CUDA_OK(cudaMallocAsync(&a.tab, sizeof(cplx<T>) * (size_t)NZ * a.ntab, s));
+    dim3 grid((unsigned)((a.HP + SHEPZ_COLS - 1) / SHEPZ_COLS), (unsigned)(H + 1));
+    kern<<<grid, 256, smem, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    int rc = 0;
+    if (e != cudaSuccess) { set_error(std::string("sheppard_zplanes_kernel: ") + cudaGetErrorString(e)); rc = 2; }
+    if (!rc) rc = hanser_launch_tables<T>(N, -H, a.tab, NZ, psfa_out, psfi_out, s);
+    cudaFreeAsync(a.tab, s);
+    return rc;
+}
+
 int fft_twiddles_f32(int L, const void** out, cudaStream_t s);   // fftnd_f32.cu / fftnd_f64.cu
 int fft_twiddles_f64(int L, const void** out, cudaStream_t s);
 
@@ -176,13 +333,8 @@ int sheppard_fused(const SheppardParams& p, void* psfa_out, void* psfi_out, cuda
     PYOTF_REQUIRE(nvox < ((size_t)1 << 31), "sheppard: volumes of 2^31 voxels or more are not supported");
     cplx<T>* tmp = nullptr;
     unsigned char* planeflag = nullptr;
-    PYOTF_CUDA_OK(cudaMallocAsync(&tmp, nvox * sizeof(cplx<T>), s));
-    PYOTF_CUDA_OK(cudaMallocAsync(&planeflag, (size_t)p.NZ * p.N, s));
-    // line flags of passes 2 / 3: line (zm, xm) may hold data iff plane zm may hold shell voxels
-    sheppard_planeflag_kernel<<<(unsigned)(((size_t)p.NZ * p.N + 255) / 256), 256, 0, s>>>(p, planeflag);
-    PYOTF_CUDA_OK(cudaGetLastError());
     ShepArgs<T> a;
-    a.p = p; a.tmp = tmp; a.planeflag = planeflag;
+    a.p = p;
     {
         // the predicate of sheppard_planeflag_kernel on the host: the occupied planes as runs of the memory index zm
         a.band0[0] = a.band0[1] = 0; a.bandn[0] = a.bandn[1] = 0;
@@ -200,6 +352,17 @@ int sheppard_fused(const SheppardParams& p, void* psfa_out, void* psfi_out, cuda
         }
         if (runs > 2) a.bandn[0] = -1;
     }
+    {
+        // scalar model, power-of-two sizes: z-first evaluation through the HanserPSF kernel
+        const int rcz = sheppard_zfirst<T>(p, a.band0, a.bandn, psfa_out, psfi_out, s);
+        if (rcz != 3) return rcz;
+    }
+    PYOTF_CUDA_OK(cudaMallocAsync(&tmp, nvox * sizeof(cplx<T>), s));
+    PYOTF_CUDA_OK(cudaMallocAsync(&planeflag, (size_t)p.NZ * p.N, s));
+    // line flags of passes 2 / 3: line (zm, xm) may hold data iff plane zm may hold shell voxels
+    sheppard_planeflag_kernel<<<(unsigned)(((size_t)p.NZ * p.N + 255) / 256), 256, 0, s>>>(p, planeflag);
+    PYOTF_CUDA_OK(cudaGetLastError());
+    a.tmp = tmp; a.planeflag = planeflag;
     const void *twx = nullptr, *twz = nullptr;
     int rc = sizeof(T) == 4 ? fft_twiddles_f32(p.N, &twx, s) : fft_twiddles_f64(p.N, &twx, s);
     if (!rc) rc = sizeof(T) == 4 ? fft_twiddles_f32(p.NZ, &twz, s) : fft_twiddles_f64(p.NZ, &twz, s);

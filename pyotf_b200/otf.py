@@ -282,10 +282,14 @@ class HanserPSF(BasePSF):
     # -- hooks used by phase retrieval / aberration code (pyotf/otf.py:335-360) ------------
     def _gen_kr(self):
         """Pupil-plane coordinates (unshifted): ``_k, _kr, _phi, _kmag, _kz``."""
+        key = (self.wl, self.ni, self.res, self.size)
+        if self.__dict__.get("_kr_key") == key:         # same geometry as the last call: the arrays are still right
+            return
         self._k = np.fft.fftfreq(self.size, self.res)
         kr, phi, kz = _engine.hanser_kspace(self.wl, self.ni, self.res, self.size)
         self._kr, self._phi, self._kz = kr.cpu().numpy(), phi.cpu().numpy(), kz.cpu().numpy()
         self._kmag = self.ni / self.wl
+        self.__dict__["_kr_key"] = key
 
     def _gen_pupil(self):
         """Ideal pupil: complex ones where kr <= na / wl (pyotf/otf.py:346-355)."""

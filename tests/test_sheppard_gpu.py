@@ -102,3 +102,29 @@ def test_cfg3_golden(precision):
         assert rel_l2(s.OTFi[:, 128, :], g["otfi_zx"]) <= tol
         s._gen_kr()
         assert s.dk == float(g["dk"]) and s.dkz == float(g["dkz"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("size,zsize,dual,na", [(32, 32, False, 1.27), (64, 32, True, 1.27), (128, 64, False, 0.85),
+                                                (256, 64, False, 1.27), (64, 128, False, 1.1)])
+def test_z_first_path_matches_oracle_and_three_pass(precision, size, zsize, dual, na, monkeypatch):
+    """Scalar model at power-of-two sizes: the z-first evaluation (direct z transform of the few shell voxels per
+    (ky, kx) column into compact per-plane pupils, then the HanserPSF kernel K1 per plane) against the oracle
+    (numpy ifftn of the reference's shell, otf.py:497-592, :204-207) and against the three-pass path."""
+    from oracle import pyotf_oracle as orc
+    from pyotf_b200.otf import SheppardPSF
+
+    kw = dict(wl=520, na=na, ni=1.33, res=100, size=size, zres=190, zsize=zsize)
+    tol = TOL[precision]
+    o = orc.sheppard_otfa(kw["wl"], kw["na"], kw["ni"], kw["res"], kw["size"], kw["zres"], kw["zsize"], "none", "none", dual)
+    assert np.count_nonzero(o) > 10
+    want_a = orc.sheppard_psfa(o)
+    monkeypatch.delenv("PYOTF_B200_SHEPPARD_3PASS", raising=False)
+    s = SheppardPSF(dual=dual, precision=precision, **kw)
+    psfi = s.PSFi                                  # fresh model: PSFi straight from the fused path
+    assert rel_l2(psfi, orc.psfi(want_a)) <= tol
+    s2 = SheppardPSF(dual=dual, precision=precision, **kw)
+    assert rel_l2(s2.PSFa, want_a) <= tol
+    monkeypatch.setenv("PYOTF_B200_SHEPPARD_3PASS", "1")
+    s3 = SheppardPSF(dual=dual, precision=precision, **kw)
+    assert rel_l2(s3.PSFi, psfi) <= 2 * tol

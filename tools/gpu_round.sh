@@ -23,10 +23,14 @@ python tools/prof_cmd.py k1 --precision=fp64 > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'hanser_sym_kernel' -s 1 -c 1 -f \
     -o gpurun_out/k1f64_$TAG python tools/prof_cmd.py k1 --precision=fp64 > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "K1 fp64 capture rc=$?"
+# one iteration per launch for the capture (the shipped loop runs up to 8 behind in-kernel barriers: same kernel code),
+# so that the per-launch counters are per-iteration counters
+export PYOTF_B200_PR_ITERS_PER_LAUNCH=1
 python tools/prof_cmd.py pr > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'pr_plane' -s 2 -c 1 -f \
     -o gpurun_out/pr_$TAG python tools/prof_cmd.py pr > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "K2 capture rc=$?"
+unset PYOTF_B200_PR_ITERS_PER_LAUNCH
 python tools/prof_cmd.py big bigsym otf sheppard > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none -k regex:'hanser_big|rfft_z|cfft_rows|fft_lines' -c 20 -f \
     -o gpurun_out/other_$TAG python tools/prof_cmd.py big bigsym otf sheppard > gpurun_out/ncu_full_$TAG.log 2>&1
