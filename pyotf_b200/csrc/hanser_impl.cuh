@@ -463,9 +463,14 @@ int hanser_launch(const pyotf_hanser* h, const double* z, int nz, const void* pu
 // SheppardPSF cap is at every z, sheppard_impl.cuh).  Runs the even-symmetric variant of the fused kernel (half the
 // columns, half the rows).  psfa [nz][N][N] and / or psfi = |psfa|^2.  Returns 3 when the support box does not fit the
 // fused on-chip kernel (the caller falls back).
-template <typename T> __global__ void hanser_zero_z_kernel(double* __restrict__ z, int n) {
+template <typename T> __global__ void hanser_tables_prep_kernel(int N, cplx<T>* __restrict__ tw, double* __restrict__ z, int nz) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) z[i] = 0.0;
+    if (i < N) {                                       // tw[k] = e^{+2 pi i k / N} (twiddle_kernel)
+        double sn, cs;
+        sincospi(2.0 * (double)i / (double)N, &sn, &cs);
+        tw[i] = mk<T>((T)cs, (T)sn);
+    }
+    if (i < nz) z[i] = 0.0;                            // the tables are final: no plane position enters
 }
 
 template <typename T>
@@ -493,8 +498,7 @@ int hanser_launch_tables(int N, int f0, const void* tables, int nz, void* psfa, 
     PYOTF_CUDA_OK(cudaMallocAsync(&tmp, tw_bytes + sizeof(double) * (size_t)nz, s));
     cplx<T>* tw = (cplx<T>*)tmp;
     double* z = (double*)(tmp + tw_bytes);
-    twiddle_kernel<T><<<(N + 255) / 256, 256, 0, s>>>(N, tw);
-    hanser_zero_z_kernel<T><<<(nz + 255) / 256, 256, 0, s>>>(z, nz);      // the tables are final: no plane position enters
+    hanser_tables_prep_kernel<T><<<(std::max(N, nz) + 255) / 256, 256, 0, s>>>(N, tw, z, nz);
     PYOTF_CUDA_OK(cudaGetLastError());
     HanserArgs<T> a;
     memset(&a, 0, sizeof(a));

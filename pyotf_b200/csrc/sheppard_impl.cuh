@@ -179,7 +179,7 @@ template <typename T, bool FAST = false> struct ShepCol : NoAcc {
 // sheppard_zplanes_kernel writes the tables ([zm][dtab_size], 8.5 MB at config 3) and K1 (hanser_launch_tables)
 // turns every plane into PSFa / PSFi on chip: the 134 MB volume is never formed, the only large traffic is the output.
 //
-// CTA = (16 columns ax0 .. ax0 + 15 of quadrant row ay).  Phase A: the shell voxels of each column as a list (freq
+// CTA = (8 columns ax0 .. ax0 + 7 of quadrant row ay, one per warp).  Phase A: the shell voxels of each column as a list (freq
 // index, value), the predicates evaluated on the occupied kz planes only.  Phase B: lanes = 32 consecutive z, direct
 // sum over the column's list into a shared tile [z][col].  Phase C: the tile goes out row by row.
 template <typename T> struct ShepZArgs {
@@ -190,7 +190,7 @@ template <typename T> struct ShepZArgs {
     double scale;               // 1 / NZ
 };
 
-constexpr int SHEPZ_COLS = 16, SHEPZ_ZC = 256, SHEPZ_TP = SHEPZ_COLS + 1;
+constexpr int SHEPZ_COLS = 8, SHEPZ_ZC = 256, SHEPZ_TP = SHEPZ_COLS + 1;   // 8 columns per CTA: one per warp (the phases are latency-bound chains)
 
 template <typename T>
 __global__ void __launch_bounds__(256) sheppard_zplanes_kernel(ShepZArgs<T> a) {
@@ -211,58 +211,82 @@ __global__ void __launch_bounds__(256) sheppard_zplanes_kernel(ShepZArgs<T> a) {
         sincospi(2.0 * (double)k / (double)NZ, &sn, &cs);
         tw[k] = mk<T>((T)cs, (T)sn);
     }
-    // ---- phase A: column lists ----
+    // ---- phase A: column lists.  A lane evaluates up to NCH band planes of each of the warp's columns as independent
+    //      chains (the fp64 predicates are latency-bound), then the survivors are compacted with ballots ----
     const double ky = __dmul_rn((double)ay, p.kstep);
-    for (int c = warp * CPW; c < warp * CPW + CPW; ++c) {
-        const int ax = ax0 + c;
-        const double kx = __dmul_rn((double)ax, p.kstep);
-        int count = 0;
-        if (ax <= a.H) {                                                    // (the pitch's padding column stays zero)
-            for (int b0 = 0; b0 < nband; b0 += 32) {
-                const int b = b0 + lane;
-                T val = (T)0;
-                int zu = 0;
-                if (b < nband) {
-                    const int zm = b < a.bandn[0] ? a.band0[0] + b : a.band0[1] + (b - a.bandn[0]);
-                    zu = zm - NZ / 2; if (zu < 0) zu += NZ;                 // unshifted frequency index
-                    const double kz = fftfreq_at(zu, NZ, p.kzstep);
-                    const double r2zy = __dadd_rn(__dmul_rn(kz, kz), __dmul_rn(ky, ky));
-                    val = sheppard_shell_value<T>(p, 0, kz, ky, kx, r2zy);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, val != (T)0);
-                if (val != (T)0) {
-                    const int pos = count + __popc(m & ((1u << lane) - 1u));
-                    lval[c * nband + pos] = val; lidx[c * nband + pos] = zu;
-                }
-                count += __popc(m);
+    constexpr int NCH = 4;
+    int count[CPW];
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) count[j] = 0;
+    for (int b0 = 0; b0 < nband; b0 += 32 * NCH) {
+        T val[CPW][NCH];
+        int zu[NCH];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+            const int b = b0 + 32 * q + lane;
+            const bool on = b < nband;
+            const int zm = b < a.bandn[0] ? a.band0[0] + b : a.band0[1] + (b - a.bandn[0]);
+            zu[q] = zm - NZ / 2; if (zu[q] < 0) zu[q] += NZ;            // unshifted frequency index
+            const double kz = fftfreq_at(on ? zu[q] : 0, NZ, p.kzstep);
+            const double r2zy = __dadd_rn(__dmul_rn(kz, kz), __dmul_rn(ky, ky));
+#pragma unroll
+            for (int j = 0; j < CPW; ++j) {
+                const int ax = ax0 + warp * CPW + j;
+                const double kx = __dmul_rn((double)ax, p.kstep);
+                val[j][q] = (on && ax <= a.H) ? sheppard_shell_value<T>(p, 0, kz, ky, kx, r2zy) : (T)0;   // (padding column: zero)
             }
         }
-        if (lane == 0) nnz[c] = count;
+#pragma unroll
+        for (int j = 0; j < CPW; ++j) {
+            const int c = warp * CPW + j;
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+                const unsigned m = __ballot_sync(0xffffffffu, val[j][q] != (T)0);
+                if (val[j][q] != (T)0) {
+                    const int pos = count[j] + __popc(m & ((1u << lane) - 1u));
+                    lval[c * nband + pos] = val[j][q]; lidx[c * nband + pos] = zu[q];
+                }
+                count[j] += __popc(m);
+            }
+        }
     }
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) if (lane == 0) nnz[warp * CPW + j] = count[j];
     __syncthreads();
     const T scale = (T)a.scale;
     for (int zb = 0; zb < NZ; zb += ZC) {
-        // ---- phase B: direct z transform of the warp's columns, lanes = consecutive z ----
+        // ---- phase B: direct z transform of the warp's columns; a lane carries ZU values of z (z, z + 32, ...) so that
+        //      the list entries are read once and the table lookups are independent ----
+        constexpr int ZU = 4;
         for (int c = warp * CPW; c < warp * CPW + CPW; ++c) {
             const int n = nnz[c];
             const T* __restrict__ lv = lval + c * nband;
             const int* __restrict__ li = lidx + c * nband;
-            for (int zg = 0; zg < ZC; zg += 32) {
-                const int z = zb + zg + lane;
-                T sx = 0, sy = 0;
+            for (int zg = 0; zg < ZC; zg += 32 * ZU) {
+                T sx[ZU], sy[ZU];
+#pragma unroll
+                for (int u = 0; u < ZU; ++u) { sx[u] = 0; sy[u] = 0; }
                 for (int e = 0; e < n; ++e) {
-                    const cplx<T> t = tw[(li[e] * z) & (NZ - 1)];
-                    sx += lv[e] * t.x; sy += lv[e] * t.y;
+                    const int k = li[e];
+                    const T v = lv[e];
+#pragma unroll
+                    for (int u = 0; u < ZU; ++u) {
+                        const cplx<T> t = tw[(k * (zb + zg + 32 * u + lane)) & (NZ - 1)];
+                        sx[u] += v * t.x; sy[u] += v * t.y;
+                    }
                 }
-                tile[(zg + lane) * SHEPZ_TP + c] = mk<T>(sx * scale, sy * scale);
+#pragma unroll
+                for (int u = 0; u < ZU; ++u)
+                    if (zg + 32 * u < ZC) tile[(zg + 32 * u + lane) * SHEPZ_TP + c] = mk<T>(sx[u] * scale, sy[u] * scale);
             }
         }
         __syncthreads();
         // ---- phase C: rows of the tile -> table of plane zm = (z + NZ / 2) mod NZ (fftshift along z) ----
         {
-            const int c = lane & (SHEPZ_COLS - 1), half = lane / SHEPZ_COLS;         // two z rows per warp pass
+            constexpr int RPW = 32 / SHEPZ_COLS;                                      // z rows per warp pass
+            const int c = lane & (SHEPZ_COLS - 1);
             if (ax0 + c < a.HP) {
-                for (int zz = warp * 2 + half; zz < ZC; zz += 16) {
+                for (int zz = warp * RPW + lane / SHEPZ_COLS; zz < ZC; zz += 8 * RPW) {
                     const int zm = (zb + zz + NZ / 2) & (NZ - 1);
                     a.tab[(size_t)zm * a.ntab + ay * a.HP + ax0 + c] = tile[zz * SHEPZ_TP + c];
                 }
