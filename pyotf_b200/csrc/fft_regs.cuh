@@ -21,6 +21,31 @@ template <> struct vec2<double> { using type = double2; };
 template <typename T> __device__ __forceinline__ cplx<T> mk(T a, T b) { cplx<T> r; r.x = a; r.y = b; return r; }
 template <typename T> __device__ __forceinline__ cplx<T> operator+(cplx<T> a, cplx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
 template <typename T> __device__ __forceinline__ cplx<T> operator-(cplx<T> a, cplx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+#ifndef PYOTF_SCALAR_F32      // -DPYOTF_SCALAR_F32: two FADDs per complex addition (A/B builds)
+// Packed FP32 (sm_100a): a complex addition / subtraction is ONE add.f32x2 / sub.f32x2 on the (x, y) register pair --
+// the same IEEE result per component as two FADDs at half the issue slots (tools/_dbg/f32x2_bench.cu: both forms run
+// at the same 128 FP32 lanes per clock per SM).  The butterflies' additions are a third of the instructions of the
+// issue-bound FFT kernels.  Measured (bench.py): K1s 7.01 -> 6.62 us per 128-plane stack (73 -> 77 % of the HBM peak),
+// the 1024^2 passes +3 %, everything else unchanged; all parity tests bit-for-bit as before where they compare kernels.
+__device__ __forceinline__ cplx<float> operator+(cplx<float> a, cplx<float> b) {
+    unsigned long long pa, pb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(pa) : "l"(pb));
+    cplx<float> r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pa));
+    return r;
+}
+__device__ __forceinline__ cplx<float> operator-(cplx<float> a, cplx<float> b) {
+    unsigned long long pa, pb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(pa) : "l"(pb));
+    cplx<float> r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pa));
+    return r;
+}
+#endif
 template <typename T> __device__ __forceinline__ cplx<T> cmul(cplx<T> a, cplx<T> b) {
     return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
