@@ -32,7 +32,7 @@ ncu --set full --clock-control none --import-source on -k regex:'pr_plane' -s 2 
 echo "K2 capture rc=$?"
 unset PYOTF_B200_PR_ITERS_PER_LAUNCH
 python tools/prof_cmd.py big bigsym otf sheppard > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none -k regex:'hanser_big|rfft_z|cfft_rows|fft_lines' -c 20 -f \
+ncu --set full --clock-control none -k regex:'hanser_big|rfft_z|cfft_rows|fft_lines|sheppard_zplanes|hanser_psf_kernel' -c 24 -f \
     -o gpurun_out/other_$TAG python tools/prof_cmd.py big bigsym otf sheppard > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "other kernels capture rc=$?"
 # gpurun brings back at most 64 MiB: condense the big reports here (ncu is on the box) and drop them
