@@ -314,7 +314,7 @@ int sheppard_zfirst(const SheppardParams& p, const int band0[2], const int bandn
     const double dmax = std::fmax(p.dk, p.dkz);
     const double kxy2 = p.kmag * p.kmag - p.kz_min * p.kz_min + 2.0 * dmax * (p.kmag - p.kz_min);
     const int H = (int)std::floor(std::sqrt(kxy2) / p.kstep * (1.0 + 1e-9));
-    if (H < 1 || H >= N / 2) return 3;
+    if (H < 1 || H > N / 4) return 3;        // (wider boxes: K1's staged table / band-limited rows do not apply; three-pass path)
     ShepZArgs<T> a;
     a.p = p; a.H = H; a.HP = dtab_pitch(-H); a.ntab = dtab_size(-H);
     a.band0[0] = band0[0]; a.band0[1] = band0[1]; a.bandn[0] = bandn[0]; a.bandn[1] = bandn[1];
