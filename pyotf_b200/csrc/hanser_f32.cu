@@ -4,7 +4,7 @@ template int hanser_build_tables<float>(pyotf_hanser*, cudaStream_t);
 template int hanser_pack<float>(const pyotf_hanser*, const void*, int, void*, cudaStream_t);
 template int hanser_launch<float>(const pyotf_hanser*, const double*, int, const void*, int, long long, void*, void*,
                                   cudaStream_t, const double*);
-template int hanser_launch_tables<float>(int, int, const void*, int, void*, void*, cudaStream_t);
+template int hanser_launch_tables<float>(int, int, const void*, int, void*, void*, cudaStream_t, const void*);
 }  // namespace pyotf
 
 #ifdef PYOTF_K1_TIMING

@@ -473,8 +473,12 @@ template <typename T> __global__ void hanser_tables_prep_kernel(int N, cplx<T>* 
     if (i < nz) z[i] = 0.0;                            // the tables are final: no plane position enters
 }
 
+// tw_z: optional device buffer the caller has ALREADY filled with K1's N twiddles e^{+2 pi i k / N} (cplx<T>[N]) followed,
+// 8-byte aligned, by nz zeros (double[nz]) -- hanser_tables_aux_bytes() -- so that no preparation launch is needed here.
+inline size_t hanser_tables_aux_bytes(int N, int nz, size_t cplx_bytes) { return cplx_bytes * (size_t)N + sizeof(double) * (size_t)nz; }
+
 template <typename T>
-int hanser_launch_tables(int N, int f0, const void* tables, int nz, void* psfa, void* psfi, cudaStream_t s) {
+int hanser_launch_tables(int N, int f0, const void* tables, int nz, void* psfa, void* psfi, cudaStream_t s, const void* tw_z) {
     if (!(N == 32 || N == 64 || N == 128 || N == 256) || f0 >= 0 || -f0 >= N / 2 || nz < 1 || nz > 16383) return 3;
     pyotf_hanser hd;                                   // the launch layers read the geometry and the device only
     PYOTF_CUDA_OK(cudaGetDevice(&hd.device));
@@ -495,11 +499,14 @@ int hanser_launch_tables(int N, int f0, const void* tables, int nz, void* psfa, 
     keep_scratch_pool();
     char* tmp = nullptr;
     const size_t tw_bytes = sizeof(cplx<T>) * (size_t)N;
-    PYOTF_CUDA_OK(cudaMallocAsync(&tmp, tw_bytes + sizeof(double) * (size_t)nz, s));
-    cplx<T>* tw = (cplx<T>*)tmp;
-    double* z = (double*)(tmp + tw_bytes);
-    hanser_tables_prep_kernel<T><<<(std::max(N, nz) + 255) / 256, 256, 0, s>>>(N, tw, z, nz);
-    PYOTF_CUDA_OK(cudaGetLastError());
+    const cplx<T>* tw = (const cplx<T>*)tw_z;
+    const double* z = tw_z ? (const double*)((const char*)tw_z + tw_bytes) : nullptr;
+    if (!tw_z) {
+        PYOTF_CUDA_OK(cudaMallocAsync(&tmp, hanser_tables_aux_bytes(N, nz, sizeof(cplx<T>)), s));
+        hanser_tables_prep_kernel<T><<<(std::max(N, nz) + 255) / 256, 256, 0, s>>>(N, (cplx<T>*)tmp, (double*)(tmp + tw_bytes), nz);
+        PYOTF_CUDA_OK(cudaGetLastError());
+        tw = (const cplx<T>*)tmp; z = (const double*)(tmp + tw_bytes);
+    }
     HanserArgs<T> a;
     memset(&a, 0, sizeof(a));
     a.tw = tw; a.dtab = (const cplx<T>*)tables; a.z = z;
@@ -513,7 +520,7 @@ int hanser_launch_tables(int N, int f0, const void* tables, int nz, void* psfa, 
         case 128: rc = hanser_launch_n<T, 128>(&hd, a, 1, 1, smem_limit, s); break;
         default:  rc = hanser_launch_n<T, 256>(&hd, a, 1, 1, smem_limit, s); break;
     }
-    cudaFreeAsync(tmp, s);
+    if (tmp) cudaFreeAsync(tmp, s);
     return rc;
 }
 

@@ -188,6 +188,8 @@ template <typename T> struct ShepZArgs {
     int band0[2], bandn[2];     // the occupied kz planes as runs of the fftshift-ed index zm
     cplx<T>* tab;               // [NZ][ntab]
     double scale;               // 1 / NZ
+    cplx<T>* twn;               // [N] e^{+2 pi i k / N} followed by NZ zero doubles: what K1 needs besides the tables
+                                // (hanser_tables_aux_bytes), written by CTA (0, 0) so that no extra launch prepares it
 };
 
 constexpr int SHEPZ_COLS = 8, SHEPZ_ZC = 256, SHEPZ_TP = SHEPZ_COLS + 1;   // 8 columns per CTA: one per warp (the phases are latency-bound chains)
@@ -210,6 +212,15 @@ __global__ void __launch_bounds__(256) sheppard_zplanes_kernel(ShepZArgs<T> a) {
         double sn, cs;
         sincospi(2.0 * (double)k / (double)NZ, &sn, &cs);
         tw[k] = mk<T>((T)cs, (T)sn);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int k = tid; k < p.N; k += 256) {
+            double sn, cs;
+            sincospi(2.0 * (double)k / (double)p.N, &sn, &cs);
+            a.twn[k] = mk<T>((T)cs, (T)sn);
+        }
+        double* zz = reinterpret_cast<double*>(a.twn + p.N);
+        for (int k = tid; k < NZ; k += 256) zz[k] = 0.0;
     }
     // ---- phase A: column lists.  A lane evaluates up to NCH band planes of each of the warp's columns as independent
     //      chains (the fp64 predicates are latency-bound), then the survivors are compacted with ballots ----
@@ -296,9 +307,9 @@ __global__ void __launch_bounds__(256) sheppard_zplanes_kernel(ShepZArgs<T> a) {
     }
 }
 
-template <typename T> int hanser_launch_tables(int N, int f0, const void* tables, int nz, void* psfa, void* psfi, cudaStream_t s);
-extern template int hanser_launch_tables<float>(int, int, const void*, int, void*, void*, cudaStream_t);
-extern template int hanser_launch_tables<double>(int, int, const void*, int, void*, void*, cudaStream_t);
+template <typename T> int hanser_launch_tables(int N, int f0, const void* tables, int nz, void* psfa, void* psfi, cudaStream_t s, const void* tw_z);
+extern template int hanser_launch_tables<float>(int, int, const void*, int, void*, void*, cudaStream_t, const void*);
+extern template int hanser_launch_tables<double>(int, int, const void*, int, void*, void*, cudaStream_t, const void*);
 
 // returns 0 (done), 3 (configuration outside this path: the caller runs the three-pass evaluation) or an error
 template <typename T>
@@ -333,13 +344,15 @@ int sheppard_zfirst(const SheppardParams& p, const int band0[2], const int bandn
         configured[dev_slot] = smem;
     }
     keep_scratch_pool();
-    PYOTF_CUDA_OK(cudaMallocAsync(&a.tab, sizeof(cplx<T>) * (size_t)NZ * a.ntab, s));
+    const size_t tab_bytes = sizeof(cplx<T>) * (size_t)NZ * a.ntab;
+    PYOTF_CUDA_OK(cudaMallocAsync(&a.tab, tab_bytes + hanser_tables_aux_bytes(N, NZ, sizeof(cplx<T>)), s));
+    a.twn = reinterpret_cast<cplx<T>*>(reinterpret_cast<char*>(a.tab) + tab_bytes);
     dim3 grid((unsigned)((a.HP + SHEPZ_COLS - 1) / SHEPZ_COLS), (unsigned)(H + 1));
     kern<<<grid, 256, smem, s>>>(a);
     cudaError_t e = cudaGetLastError();
     int rc = 0;
     if (e != cudaSuccess) { set_error(std::string("sheppard_zplanes_kernel: ") + cudaGetErrorString(e)); rc = 2; }
-    if (!rc) rc = hanser_launch_tables<T>(N, -H, a.tab, NZ, psfa_out, psfi_out, s);
+    if (!rc) rc = hanser_launch_tables<T>(N, -H, a.tab, NZ, psfa_out, psfi_out, s, a.twn);
     cudaFreeAsync(a.tab, s);
     return rc;
 }
