@@ -43,21 +43,32 @@ extern "C" int pyotf_b200_unwrap_phase_2d(const double* in, double* out, int ny,
     std::vector<double> v(n), rel(n);
     // rows that are entirely zero (the region outside the aperture of a retrieved pupil): where three
     // consecutive rows are, every second difference -- hence the reliability -- is exactly 0
-    std::vector<unsigned char> rowzero(ny);
+    // per row: the span [first, last] of its non-zero samples (first = nx, last = -1: none).  A pixel whose 3 x 3
+    // neighbourhood is entirely zero has every second difference -- hence its reliability -- exactly 0.
+    std::vector<int> first(ny), last(ny);
     for (int y = 0; y < ny; ++y) {
-        bool z = true;
-        for (int x = 0; x < nx; ++x) { const double w = wrap(in[y * nx + x]); v[y * nx + x] = w; z = z && w == 0.0; }
-        rowzero[y] = z;                                   // (np.angle output is already in [-pi, pi])
+        int lo = nx, hi = -1;
+        for (int x = 0; x < nx; ++x) {
+            const double w = wrap(in[y * nx + x]);        // (np.angle output is already in [-pi, pi])
+            v[y * nx + x] = w;
+            if (w != 0.0) { if (lo == nx) lo = x; hi = x; }
+        }
+        first[y] = lo; last[y] = hi;
     }
     for (int y = 0; y < ny; ++y) {
-        const bool flat = y > 0 && y < ny - 1 && rowzero[y - 1] && rowzero[y] && rowzero[y + 1];
+        // columns x with zlo <= x <= zhi may see a non-zero sample of rows y - 1 .. y + 1
+        int zlo = nx, zhi = -1;
+        if (y > 0 && y < ny - 1) {
+            zlo = std::min(first[y - 1], std::min(first[y], first[y + 1])) - 1;
+            zhi = std::max(last[y - 1], std::max(last[y], last[y + 1])) + 1;
+        }
         for (int x = 0; x < nx; ++x) {
             const int i = y * nx + x;
             if (y == 0 || x == 0 || y == ny - 1 || x == nx - 1) {
                 rel[i] = 1e7 + (double)((uint32_t)i * 2654435761u >> 8);    // borders last, deterministic order
                 continue;
             }
-            if (flat) { rel[i] = 0.0; continue; }
+            if (x < zlo || x > zhi) { rel[i] = 0.0; continue; }
             const double c = v[i];
             const double H = wrap(v[i - 1] - c) - wrap(c - v[i + 1]);
             const double V = wrap(v[i - nx] - c) - wrap(c - v[i + nx]);
