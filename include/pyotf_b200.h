@@ -189,7 +189,8 @@ int pyotf_b200_pr_destroy(pyotf_pr_t* s);
 int pyotf_b200_pr_info(const pyotf_pr_t* s, int* K, int* rows, int* f0, int* rows_per_cta, int* nparts);
 /* Kernel launches one iteration of pyotf_b200_pr_run takes on this state (loop body of phaseretrieval.py:95-130):
  * 1 = the plane kernel finalizes the iteration itself behind a grid-wide arrival barrier (single GPU, every CTA
- * resident); 2 = plane kernel + finalize kernel (long stacks; z-sharded runs with a peer window, where the finalize
+ * resident) -- an upper bound: one launch then runs up to 8 iterations back to back, a second grid barrier between
+ * them (PYOTF_B200_PR_ITERS_PER_LAUNCH=1: one launch per iteration); 2 = plane kernel + finalize kernel (long stacks; z-sharded runs with a peer window, where the finalize
  * kernel also sums over the ranks); 3 = z-sharded with the NCCL fallback; 5 = the four-pass path of other sizes. */
 int pyotf_b200_pr_kernels_per_iteration(const pyotf_pr_t* s, int sharded, int* n);
 /* Inspection hook for the parity tests: device pointers of the intermediates of the last iteration
